@@ -1,0 +1,143 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference classes (TEST INFRASTRUCTURE ONLY).
+
+Run in the build container, where /root/reference exists:
+
+    python oracle/make_golden.py
+
+Each fixture holds: the config (json), a seeded synthetic batch following the batch contract
+(user_id i64 [B], item_id i64 [B,1+K] positive first, label i32 [B,1+K], item_seq i32
+[B,L] left-padded with 0, item_seq_len i64 [B]), the model's state_dict as initialised by the
+reference constructors under `general.init_seed(seed)`, and the reference outputs: loss (mean and
+per-sample), scores, user_emb, dense parameter gradients, and a 3-step dense-Adam trajectory
+(losses + final parameters) following unirec/facility/trainer.py:340-349.
+
+The GPU box has no /root/reference; only the .npz files travel.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get('UNIREC_REFERENCE', '/root/reference')
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+BASE = dict(dataset='example', exp_name='golden', train_file_format='user-item',
+            hidden_dropout_prob=0.0, attn_dropout_prob=0.0, dropout_prob=0.0, scheduler='none')
+
+CASES = {
+    'sasrec_softmax': dict(model='SASRec', n_items=211, n_users=37, embedding_size=32, hidden_size=32,
+                           n_layers=2, n_heads=2, inner_size=64, max_seq_len=8, loss_type='softmax',
+                           K=5, B=6, init_std=0.2),
+    'sasrec_bpr_nopos_bias': dict(model='SASRec', n_items=157, n_users=29, embedding_size=64, hidden_size=64,
+                                  n_layers=1, n_heads=4, inner_size=96, max_seq_len=11, loss_type='bpr',
+                                  use_position_emb=0, hidden_act='gelu', tau=0.7, has_user_bias=True,
+                                  has_item_bias=True, score_clip_value=0.05, K=3, B=5),
+    'sasrec_softmax_d128': dict(model='SASRec', n_items=301, n_users=11, embedding_size=128, hidden_size=128,
+                                n_layers=1, n_heads=2, inner_size=256, max_seq_len=50, loss_type='softmax',
+                                K=16, B=4, hidden_act='swish', init_std=0.1),
+    'gru_bpr': dict(model='GRU', n_items=123, n_users=19, embedding_size=32, hidden_size=64,
+                    max_seq_len=7, loss_type='bpr', K=5, B=6, init_std=0.3),
+    'gru_softmax_h32': dict(model='GRU', n_items=99, n_users=19, embedding_size=32, hidden_size=32,
+                            max_seq_len=5, loss_type='softmax', K=4, B=3, tau=0.5),
+    'avghist_softmax': dict(model='AvgHist', n_items=173, n_users=23, embedding_size=32,
+                            max_seq_len=12, loss_type='softmax', K=7, B=6, init_std=0.3),
+    'avghist_sym_bpr': dict(model='AvgHist', n_items=173, n_users=23, embedding_size=64, asymmetric=False,
+                            max_seq_len=9, loss_type='bpr', K=2, B=5),
+    'svdpp_bpr': dict(model='SVDPlusPlus', n_items=143, n_users=31, embedding_size=32,
+                      max_seq_len=10, loss_type='bpr', K=5, B=7),
+    'mf_bpr': dict(model='MF', n_items=97, n_users=41, embedding_size=64, loss_type='bpr', K=1, B=16, init_std=0.3),
+    'mf_softmax_bias': dict(model='MF', n_items=97, n_users=41, embedding_size=32, loss_type='softmax',
+                            has_item_bias=True, K=6, B=9, tau=2.0),
+}
+
+
+def make_batch(cfg, B, K, L, gen):
+    V, U = cfg['n_items'], cfg['n_users']
+    user_id = torch.randint(1, U, (B,), generator=gen, dtype=torch.int64)
+    item_id = torch.randint(1, V, (B, 1 + K), generator=gen, dtype=torch.int64)
+    # edge cases the reference data path produces: a failed negative draw yields id 0
+    # (addnegsamples.py:99-107); duplicated negatives; a target that also sits in the history.
+    if K >= 2:
+        item_id[0, K] = 0
+        item_id[1, 2] = item_id[1, 1]
+    label = torch.zeros(B, 1 + K, dtype=torch.int32)
+    label[:, 0] = 1
+    item_seq = torch.zeros(B, L, dtype=torch.int32)
+    lens = torch.randint(1, L + 1, (B,), generator=gen, dtype=torch.int64)
+    lens[0] = L
+    if B > 1:
+        lens[1] = 1
+    for b in range(B):
+        n = int(lens[b])
+        item_seq[b, L - n:] = torch.randint(1, V, (n,), generator=gen, dtype=torch.int64).to(torch.int32)
+    if B > 2 and L > 1:
+        item_seq[2, L - 1] = item_id[2, 0].to(torch.int32)
+    return dict(user_id=user_id, item_id=item_id, label=label, item_seq=item_seq, item_seq_len=lens)
+
+
+def main():
+    sys.path.insert(0, REF)
+    from unirec.utils import argument_parser, general
+    os.makedirs(OUT, exist_ok=True)
+    saved_argv, sys.argv = sys.argv, sys.argv[:1]
+    for name, case in CASES.items():
+        case = dict(case)
+        B, K = case.pop('B'), case.pop('K')
+        args = dict(BASE)
+        args.update(case)
+        cfg = argument_parser.parse_arguments(args)
+        cfg['device'] = torch.device('cpu')
+        seed = 2022
+        general.init_seed(seed)
+        model = general.get_class_instance(cfg['model'], 'unirec/model')(cfg)
+        model.train()
+        L = int(cfg['max_seq_len'])
+        gen = torch.Generator().manual_seed(seed + 1)
+        batch = make_batch(cfg, B, K, L, gen)
+        if cfg['model'] == 'MF':
+            fwd_batch = {k: batch[k] for k in ('user_id', 'item_id', 'label')}
+        else:
+            fwd_batch = batch
+        out = {}
+        for k, v in model.state_dict().items():
+            out['param/' + k] = v.detach().numpy().copy()
+        loss, scores, user_emb, items_emb = model(**fwd_batch, return_loss_only=False)
+        model.zero_grad()
+        loss.backward()
+        for k, p_ in model.named_parameters():
+            g = p_.grad if p_.grad is not None else torch.zeros_like(p_)
+            out['grad/' + k] = g.detach().numpy().copy()
+        loss_vec = model(**fwd_batch, reduction=False)[0]
+        out['loss'] = loss.detach().numpy()
+        out['loss_vec'] = loss_vec.detach().numpy()
+        out['scores'] = scores.detach().numpy()
+        out['user_emb'] = user_emb.detach().numpy()
+        # 3-step dense Adam trajectory on the same batch (trainer.py:136,340-349)
+        opt = torch.optim.Adam(model.parameters(), lr=float(cfg['learning_rate']),
+                               weight_decay=float(cfg['weight_decay']))
+        traj = []
+        for _ in range(3):
+            l_ = model(**fwd_batch)[0]
+            opt.zero_grad()
+            l_.backward()
+            opt.step()
+            traj.append(float(l_.detach()))
+        out['traj_loss'] = np.asarray(traj, dtype=np.float64)
+        for k, v in model.state_dict().items():
+            out['traj_param/' + k] = v.detach().numpy().copy()
+        for k, v in batch.items():
+            out['batch/' + k] = v.numpy()
+        keep = {k: v for k, v in cfg.items()
+                if isinstance(v, (int, float, str, bool)) and k not in ('exp_name', 'config_dir')}
+        keep['K'], keep['B'] = K, B
+        out['config_json'] = np.frombuffer(json.dumps(keep, sort_keys=True).encode(), dtype=np.uint8)
+        path = os.path.join(OUT, name + '.npz')
+        np.savez_compressed(path, **out)
+        print('%-26s loss=%.6f  %7.1f KB' % (name, float(loss), os.path.getsize(path) / 1024))
+    sys.argv = saved_argv
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,62 @@
+"""CPU: the oracle restatement must reproduce the reference classes' outputs (golden fixtures)."""
+import pytest
+import torch
+
+from oracle import unirec_oracle as O
+from golden_util import CASES, Golden, rel_err
+
+
+def test_have_fixtures():
+    assert len(CASES) >= 10
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_forward_matches_reference(name):
+    g = Golden(name)
+    loss, scores, user_emb, _ = O.forward(g.model, g.params, g.cfg, **g.fwd_batch())
+    assert rel_err(scores, g.scores) < 2e-6
+    assert rel_err(user_emb, g.user_emb) < 2e-6
+    assert abs(float(loss) - float(g.loss)) <= 2e-6 * abs(float(g.loss))
+    loss_vec = O.forward(g.model, g.params, g.cfg, reduction=False, **g.fwd_batch())[0]
+    assert rel_err(loss_vec, g.loss_vec) < 2e-6
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_grads_match_reference(name):
+    g = Golden(name)
+    _, _, _, grads = O.loss_and_grads(g.model, g.params, g.cfg, g.fwd_batch())
+    scale = max(float(v.abs().max()) for v in g.grads.values())
+    for k, ref in g.grads.items():
+        # key.bias has an analytically zero gradient (softmax shift invariance): compare on the global scale
+        err = float((grads[k].double() - ref.double()).abs().max())
+        assert err <= 1e-5 * max(float(ref.abs().max()), 1e-2 * scale), k
+    # padding row of every padded table has zero gradient (nn.Embedding padding_idx=0)
+    for k in O.PADDING_TABLES:
+        if k in grads:
+            assert float(grads[k][0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_dense_adam_trajectory_matches_reference(name):
+    g = Golden(name)
+    p = O.tie_aliases(g.model, g.cfg, {k: v.clone() for k, v in g.params.items()})
+    opt = O.DenseAdam(p, lr=float(g.cfg['learning_rate']), weight_decay=float(g.cfg['weight_decay']))
+    losses = [float(O.train_step(g.model, p, g.cfg, g.fwd_batch(), opt)) for _ in range(3)]
+    for a, b in zip(losses, g.traj_loss):
+        assert abs(a - b) <= 1e-5 * abs(b)
+    for k, ref in g.traj_params.items():
+        if k.endswith('key.bias'):
+            continue    # analytically zero gradient: Adam turns rounding noise into +-lr moves (sign of noise)
+        assert rel_err(p[k], ref) < 1e-4, k
+
+
+def test_lazy_adam_equals_dense_on_touched_rows_first_step():
+    g = Golden('mf_bpr')
+    p1 = {k: v.clone() for k, v in g.params.items()}
+    p2 = {k: v.clone() for k, v in g.params.items()}
+    _, _, _, grads = O.loss_and_grads(g.model, p1, g.cfg, g.fwd_batch())
+    O.DenseAdam(p1).step(p1, grads)
+    touched = {'item_embedding.weight': g.batch['item_id'], 'user_embedding.weight': g.batch['user_id']}
+    O.LazyRowAdam(p2).step(p2, grads, touched)
+    for k in p1:
+        assert rel_err(p1[k], p2[k]) < 1e-6   # step 1: untouched rows have zero grad and zero moments
