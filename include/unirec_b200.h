@@ -1,0 +1,131 @@
+/* unirec_b200.h -- C ABI of the B200-native hot path for microsoft/UniRec's sequential-recommender training loop.
+ *
+ * The reference has no FFI: its boundary is the Python model/trainer contract.  This header is the
+ * NEW native boundary below that contract.  Every entry point names the reference code it replaces (paths relative
+ * to the reference repository root).  Conventions:
+ *   - plain device pointers and sizes; no framework types; `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, UR_ERR_* (<0) for bad arguments, -(1000+cudaError_t) for a launch error;
+ *   - no allocation, no ownership transfer, no host synchronisation, re-entrant across streams;
+ *   - all matrices row-major fp32; feature dimensions (d, hidden sizes, leading dimensions) are multiples of 4 and
+ *     pointers 16-byte aligned; id 0 is the padding row of every table (reference: nn.Embedding(padding_idx=0),
+ *     unirec/model/base/reco_abc.py:167-170).
+ */
+#ifndef UNIREC_B200_H_
+#define UNIREC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UR_ABI_VERSION 1
+
+enum { UR_LOSS_SOFTMAX = 0, UR_LOSS_BPR = 1 };
+enum { UR_ACT_NONE = 0, UR_ACT_SWISH = 1, UR_ACT_GELU = 2, UR_ACT_RELU = 3, UR_ACT_TANH = 4, UR_ACT_SIGMOID = 5 };
+enum { UR_OPT_ADAM = 0, UR_OPT_ADAMW = 1, UR_OPT_SGD = 2, UR_OPT_SQNORM = 3 };
+
+int ur_version(void);
+/* 1 when the library was built with the tcgen05 GEMM path */
+int ur_has_tensor_core_gemm(void);
+
+/* ---- K1/K2: embedding row gather.  out[i,:] = table[idx[i],:], bit-exact.
+ * replaces: item_embedding(items) unirec/model/base/recommender.py:67, :137; user_embedding(user_id) :43 */
+int ur_gather_rows_f32(const float* table, int64_t n_rows, int d, const void* idx, int idx_bits /*32|64*/, int64_t n,
+                       float* out, void* stream);
+
+/* ---- K11 (exact-dense mode): grad[idx[i],:] += coef * src[i / src_group,:], rows with idx == pad_id skipped.
+ * replaces: embedding_dense_backward under accelerator.backward, unirec/facility/trainer.py:346 */
+int ur_scatter_add_rows_f32(float* grad, int64_t n_rows, int d, const void* idx, int idx_bits, int64_t n, const float* src,
+                            int64_t src_group, const float* coef /*nullable*/, int64_t coef_group, int64_t pad_id,
+                            void* stream);
+
+/* ---- K10: sum-pool user tower. user_emb[b] = (user_table ? user_table[user_id[b]] : 0) + (len[b]+1)^-alpha * sum_l table[seq[b,l]]
+ * replaces: AvgHist.forward_user_emb unirec/model/sequential/avghist.py:34-42; SVDPlusPlus.forward_user_emb svdplusplus.py:31-39 */
+int ur_pool_sum_fwd_f32(const float* table, int d, const int32_t* item_seq, int64_t B, int L, const int64_t* item_seq_len,
+                        float alpha, const float* user_table /*nullable*/, const int64_t* user_id, float* user_emb,
+                        float* coeff_out /*[B], nullable*/, void* stream);
+
+/* ---- K1+K3: Y = LayerNorm(table[item_seq] + pos[0..L-1]); saves per-row mean / rstd.
+ * replaces: SASRec.forward_user_emb prologue, unirec/model/sequential/sasrec.py:60-69 */
+int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos /*nullable*/, const float* gamma, const float* beta, float eps,
+                           const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd, void* stream);
+/* dX[B*L,d] = gradient wrt the gathered rows (feeds the row-sparse table update); dgamma/dbeta/dpos are ACCUMULATED */
+int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* gamma, const int32_t* item_seq, int64_t B, int L,
+                           int d, const float* mean, const float* rstd, const float* dY, float* dX, float* dgamma, float* dbeta,
+                           float* dpos /*nullable*/, void* stream);
+
+/* ---- K6: post-LN residual.  X <- X + R (kept for backward), Y = LayerNorm(X).
+ * replaces: LayerNorm(hidden + input) unirec/model/modules.py:314, :353 */
+int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R /*nullable*/, int64_t ldr, const float* gamma, const float* beta,
+                      float eps, int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd, void* stream);
+/* dZ = LN'(Z) (dY + dExtra); dgamma/dbeta ACCUMULATED; dZ may alias dY */
+int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const float* mean, const float* rstd, const float* dY,
+                      int64_t lddy, const float* dExtra /*nullable*/, int64_t ldde, int64_t rows, int d, float* dZ, int64_t lddz,
+                      float* dgamma, float* dbeta, void* stream);
+
+/* ---- K4/K7: C (+)= act(op(A) op(B) + bias); preact (nullable) receives the pre-activation for backward.
+ * replaces: nn.Linear calls unirec/model/modules.py:285-287,312,348-351; gru.py:30-31
+ * ur_gemm_f32 picks the tcgen05 tensor-core kernel when the shape qualifies and precision != 0, else the exact-fp32 SIMT kernel.
+ * precision: 0 = fp32 FMA (exact path), 1 = TF32 tensor cores, 2 = BF16 tensor cores (fp32 accumulate). */
+int ur_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                float* C, int64_t ldc, const float* bias /*nullable*/, int act, float* preact /*nullable*/, int64_t ldp,
+                int accumulate, int precision, void* stream);
+int ur_gemm_simt_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
+                     void* stream);
+/* dY *= act'(preact) */
+int ur_act_bwd_f32(float* dY, const float* preact, int64_t n, int act, void* stream);
+/* out[n] += sum_m X[m,n] (bias gradients) */
+int ur_colsum_accum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* stream);
+
+/* ---- K5: fused attention on packed QKV [B*L, 3d] with the SASRec additive mask (-10000), L <= 256.
+ * replaces: MultiHeadAttention.forward unirec/model/modules.py:289-311 and SASRec._get_attention_mask sasrec.py:40-57 */
+int ur_attn_fwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
+                    float* ctx, float* lse /*[B,H,L]*/, void* stream);
+int ur_attn_bwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
+                    const float* ctx, const float* lse, const float* dctx, float* dqkv, void* stream);
+
+/* ---- K9: GRU cell pointwise parts (matrix products go through ur_gemm_f32).
+ * replaces: nn.GRU inside GRU.forward_user_emb unirec/model/sequential/gru.py:30 */
+int ur_gru_gate_fwd_f32(const float* gi, int64_t ld_gi, const float* gh, const float* h_prev, float* h_out, float* save /*[B,4H]*/,
+                        int64_t B, int H, void* stream);
+int ur_gru_gate_bwd_f32(const float* dh, const float* save, const float* h_prev, float* dgi, int64_t ld_dgi, float* dgh,
+                        float* dh_prev, int64_t B, int H, void* stream);
+
+/* ---- K8: fused target/negative gather + scores + bias/tau/clamp + loss + dLoss/dscore + dLoss/du, one pass over the rows.
+ * replaces: forward_item_emb + InnerProductScorer + _predict_layer + _cal_loss and their autograd:
+ *   unirec/model/base/recommender.py:55-59,66-96; unirec/model/modules.py:15-21,45-67; unirec/model/base/reco_abc.py:252-265
+ * norm: softmax -> number of positive labels in the batch (device scalar from ur_count_positive_i32, or norm_host);
+ *       bpr -> B*K.  loss_vec[b] is the per-sample loss term; ur_loss_finish_f32 reduces it and raises the NaN flag. */
+int ur_score_loss_fwd_bwd_f32(const float* table, int d, const float* user_emb, const int64_t* item_id, int64_t B, int N,
+                              const int32_t* label /*nullable*/, const float* item_bias /*nullable*/,
+                              const float* user_bias /*nullable*/, const int64_t* user_id, float tau, float score_clip,
+                              int loss_type, const float* norm_dev /*nullable*/, float norm_host, float* scores /*nullable*/,
+                              float* loss_vec, float* dscore /*nullable*/, float* grad_user /*nullable*/, void* stream);
+int ur_count_positive_i32(const int32_t* label, int64_t n, float* out, void* stream);
+int ur_loss_finish_f32(const float* loss_vec, int64_t B, const float* denom_dev /*nullable*/, float denom_host, float* loss_out,
+                       int32_t* nan_flag /*nullable*/, void* stream);
+
+/* ---- K11+K12+K13: row-sparse gradient reduce fused with the optimizer (see csrc/sparse_opt.cu).
+ * replaces: dense embedding grads + optim.Adam over whole tables + clip_grad_norm_, unirec/facility/trainer.py:134-152,346-349
+ * head[V] must hold -1 between steps (apply restores it); n_uniq must be zeroed by the caller before the first link of a step. */
+int ur_rowlist_link(int32_t* head, const void* keys, int idx_bits, int64_t n, int64_t entry_offset, int32_t* next, int32_t* uniq,
+                    int32_t* n_uniq, int64_t pad_id, void* stream);
+int ur_rowlist_apply_f32(float* table, float* mom, float* var, int d, int32_t* head, const int32_t* next, const int32_t* uniq,
+                         const int32_t* n_uniq, int64_t max_uniq, const float* src0, int64_t src0_group, const float* coef0,
+                         int64_t coef0_group, int64_t n0, const float* src1, int64_t src1_group, const float* coef1,
+                         int64_t coef1_group, int mode, float lr, float beta1, float beta2, float eps, float weight_decay,
+                         const int32_t* step_dev, const float* grad_scale_dev, const int32_t* skip_flag, float* sqnorm_out,
+                         void* stream);
+int ur_dense_opt_f32(float* param, const float* grad, float* mom, float* var, int64_t n, int mode, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, const int32_t* step_dev, const float* grad_scale_dev,
+                     const int32_t* skip_flag, void* stream);
+int ur_sqnorm_accum_f32(const float* grad, int64_t n, float* sqnorm, void* stream);
+int ur_clip_coef_f32(const float* sqnorm, float max_norm, float* coef, void* stream);
+int ur_step_advance(int32_t* step, const int32_t* skip_flag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIREC_B200_H_ */

@@ -1,0 +1,199 @@
+"""GPU: the drop-in model classes + trainer pieces against the reference goldens (tests/golden/*.npz, produced by the
+reference's own classes) and the CPU oracle.  Bars: loss / scores / user_emb within 1e-3 relative fp32 (north_star)."""
+import pytest
+import torch
+
+from golden_util import CASES, Golden, rel_err
+from oracle import unirec_oracle as O
+from test_host_logic import build_model
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = 1e-3
+
+
+def cuda_model(g, **over):
+    model, cfg = build_model(g, device=DEV, **over)
+    model = model.to(DEV)
+    model.load_state_dict(g.params)
+    return model, cfg
+
+
+def to_dev(batch):
+    return {k: v.to(DEV) for k, v in batch.items()}
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_forward_matches_reference(name):
+    g = Golden(name)
+    model, _ = cuda_model(g)
+    model.train()
+    loss, scores, user_emb, items_emb = model(**to_dev(g.fwd_batch()), return_loss_only=False)
+    assert abs(float(loss) - float(g.loss)) <= TOL * abs(float(g.loss))
+    assert rel_err(scores.cpu(), g.scores) < TOL
+    assert rel_err(user_emb.cpu(), g.user_emb) < TOL
+    assert torch.equal(items_emb.cpu(), O.gather_rows(g.params['item_embedding.weight'], g.batch['item_id']))   # bit-exact
+    loss_vec = model(**to_dev(g.fwd_batch()), reduction=False)[0]
+    assert rel_err(loss_vec.detach().cpu(), g.loss_vec) < TOL
+    model.eval()
+    none, s2, u2, _ = model(**to_dev(g.fwd_batch()))
+    assert none is None and rel_err(s2.cpu(), g.scores) < TOL and rel_err(u2.cpu(), g.user_emb) < TOL
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_autograd_grads_match_reference_dense_mode(name):
+    """`table_update: dense` + loss.backward(): every parameter's .grad equals the reference's dense gradient."""
+    g = Golden(name)
+    model, _ = cuda_model(g, table_update='dense')
+    model.train()
+    loss = model(**to_dev(g.fwd_batch()))[0]
+    loss.backward()
+    scale = max(float(v.abs().max()) for v in g.grads.values())
+    for k, p in model.named_parameters():
+        ref = g.grads[k]
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
+        err = float((got.double() - ref.double()).abs().max())
+        assert err <= TOL * max(float(ref.abs().max()), 1e-2 * scale), (k, err)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_dense_mode_trajectory_matches_reference_adam(name):
+    """3 steps of the fused optimizer in exact-dense mode == the reference loop with torch.optim.Adam."""
+    from unirec_b200.facility.optim import FusedOptimizer
+    g = Golden(name)
+    model, cfg = cuda_model(g, table_update='dense')
+    model.train()
+    model._ur_fast_grads = True
+    opt = FusedOptimizer(model, 'adam', lr=float(cfg['learning_rate']), weight_decay=float(cfg['weight_decay']))
+    batch = to_dev(g.fwd_batch())
+    for ref_loss in g.traj_loss:
+        loss = model(**batch)[0]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(float(loss) - ref_loss) <= TOL * abs(ref_loss)
+    sd = model.state_dict()
+    for k, ref in g.traj_params.items():
+        if k.endswith('key.bias'):
+            continue     # analytically-zero gradient: Adam amplifies rounding noise (see test_oracle_golden)
+        assert rel_err(sd[k].cpu(), ref) < 2e-3, k
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_sparse_mode_trajectory_matches_lazy_oracle(name):
+    """Default mode: row-sparse table update == oracle LazyRowAdam (dense Adam restricted to touched rows)."""
+    from unirec_b200.facility.optim import FusedOptimizer
+    g = Golden(name)
+    model, cfg = cuda_model(g)
+    model.train()
+    model._ur_fast_grads = True
+    lr = float(cfg['learning_rate'])
+    opt = FusedOptimizer(model, 'adam', lr=lr)
+    p = O.tie_aliases(g.model, g.cfg, {k: v.clone() for k, v in g.params.items()})
+    oopt = O.LazyRowAdam(p, lr=lr)
+    b = g.batch
+    seq_table = 'item_dst_embedding.weight' if (g.model == 'SVDPlusPlus' or (g.model == 'AvgHist' and g.cfg.get('asymmetric', True))) \
+        else 'item_embedding.weight'
+    touched = {'item_embedding.weight': [b['item_id'].reshape(-1)]}
+    if g.model != 'MF':
+        touched.setdefault(seq_table, []).append(b['item_seq'].reshape(-1).long())
+    if 'user_embedding.weight' in g.params:
+        touched['user_embedding.weight'] = [b['user_id']]
+    touched = {k: torch.cat(v) for k, v in touched.items()}
+    batch = to_dev(g.fwd_batch())
+    for _ in range(3):
+        loss = model(**batch)[0]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref_loss, _, _, grads = O.loss_and_grads(g.model, p, g.cfg, g.fwd_batch())
+        oopt.step(p, grads, touched)
+        assert abs(float(loss) - float(ref_loss)) <= TOL * abs(float(ref_loss))
+    sd = model.state_dict()
+    for k, ref in p.items():
+        if k.endswith('key.bias'):
+            continue
+        assert rel_err(sd[k].cpu(), ref) < 2e-3, k
+
+
+def test_grad_clipping_matches_oracle():
+    from unirec_b200.facility.optim import FusedOptimizer
+    g = Golden('sasrec_softmax')
+    model, cfg = cuda_model(g)
+    model.train()
+    model._ur_fast_grads = True
+    opt = FusedOptimizer(model, 'sgd', lr=0.5)
+    opt.max_grad_norm = 0.05
+    loss = model(**to_dev(g.fwd_batch()))[0]
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    _, _, _, grads = O.loss_and_grads(g.model, g.params, g.cfg, g.fwd_batch())
+    total = O.clip_grad_norm(grads, 0.05)
+    assert float(total) > 0.05      # the clip is active in this fixture
+    sd = model.state_dict()
+    for k, ref in g.params.items():
+        assert rel_err(sd[k].cpu(), ref - 0.5 * grads[k]) < 2e-3, k
+
+
+def test_nan_loss_skips_update_without_sync():
+    from unirec_b200.facility.optim import FusedOptimizer
+    g = Golden('mf_bpr')
+    model, cfg = cuda_model(g)
+    model.train()
+    model._ur_fast_grads = True
+    opt = FusedOptimizer(model, 'adam', lr=0.1)
+    with torch.no_grad():
+        model.user_embedding.weight[int(g.batch['user_id'][0])] = float('nan')
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    loss = model(**to_dev(g.fwd_batch()))[0]
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    assert torch.isnan(loss)
+    for k, v in model.state_dict().items():
+        assert torch.equal(torch.nan_to_num(v), torch.nan_to_num(before[k])), k
+    assert int((model._engine.rowgrad(model.item_embedding.weight).head != -1).sum()) == 0
+
+
+def test_trainer_fit_loop_and_checkpoint(tmp_path):
+    """Trainer.fit through the reference-shaped loop on a synthetic in-memory dataset (MF+BPR = BASELINE config 1 shape)."""
+    from unirec_b200.facility.accelerator import Accelerator
+    from unirec_b200.facility.trainer import Trainer
+    from unirec_b200.utils import argument_parser, general
+
+    class DS(torch.utils.data.Dataset):
+        return_key_2_index = {'user_id': 0, 'item_id': 1, 'label': 2}
+
+        def __init__(self, n, U, V, K, seed):
+            gg = torch.Generator().manual_seed(seed)
+            self.u = torch.randint(1, U, (n,), generator=gg)
+            self.i = torch.randint(1, V, (n, 1 + K), generator=gg)
+            self.i[:, 0] = (self.u * 7) % (V - 1) + 1          # learnable signal
+            self.l = torch.zeros(n, 1 + K, dtype=torch.int32)
+            self.l[:, 0] = 1
+
+        def __len__(self):
+            return len(self.u)
+
+        def __getitem__(self, k):
+            return self.u[k], self.i[k], self.l[k]
+
+    cfg = argument_parser.parse_arguments(dict(model='MF', dataset='example', exp_name='fit', n_users=200, n_items=300,
+                                               embedding_size=64, loss_type='bpr', train_file_format='user-item', epochs=3,
+                                               batch_size=256, learning_rate=0.05, scheduler='none', early_stop=0,
+                                               output_path=str(tmp_path), metrics="['hit@5','group_auc']",
+                                               key_metric='group_auc'), argv=[])
+    acc = Accelerator()
+    cfg['device'] = acc.device
+    general.init_seed(7)
+    model = general.get_class_instance('MF', 'unirec_b200/model')(cfg)
+    tr = Trainer(cfg, model, acc)
+    tr.reset_evaluator('user-item', 'one_vs_k')
+    train = torch.utils.data.DataLoader(DS(4096, 200, 300, 1, 1), batch_size=256)
+    valid = torch.utils.data.DataLoader(DS(512, 200, 300, 9, 2), batch_size=256)
+    tr.fit(train, valid, save_model=True)
+    res = tr.evaluate(valid, load_best_model=True)
+    assert res['group_auc'] > 0.8, res
+    model2, _ = general.load_model_freely(tr.saved_model_file, device=acc.device)
+    assert set(model2.state_dict()) == set(model.state_dict())

@@ -1,0 +1,94 @@
+"""CPU: host-side logic of the drop-in boundary -- config precedence, registry, seed-exact initialisation and
+state_dict names (vs the reference goldens), trainer control helpers, loud failure without CUDA."""
+import sys
+
+import pytest
+import torch
+
+from golden_util import CASES, Golden
+from unirec_b200.utils import argument_parser, general
+
+
+def _cfg(g, **over):
+    args = dict(g.cfg)
+    args.update(exp_name='t', dataset='example')
+    args.update(over)
+    cfg = argument_parser.parse_arguments(args, argv=[])
+    cfg['device'] = torch.device('cpu')
+    return cfg
+
+
+def build_model(g, device='cpu', **over):
+    cfg = _cfg(g, **over)
+    cfg['device'] = torch.device(device)
+    general.init_seed(2022)
+    return general.get_class_instance(cfg['model'], 'unirec_b200/model')(cfg), cfg
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_seeded_init_is_bit_identical_to_reference(name):
+    g = Golden(name)
+    model, _ = build_model(g)
+    sd = model.state_dict()
+    assert set(sd) == set(g.params)
+    for k in sd:
+        assert torch.equal(sd[k], g.params[k]), k
+
+
+def test_config_precedence_and_cmd_args(tmp_path):
+    f = tmp_path / 'extra.yaml'
+    f.write_text('embedding_size: 48\nlearning_rate: 0.5\n')
+    cfg = argument_parser.parse_arguments({'model': 'SASRec', 'dataset': 'example', 'learning_rate': 0.25},
+                                          argv=['--config_file', str(f), '--n_layers=3', '--bogus_flag=1', '--scheduler=none'])
+    assert cfg['n_heads'] == 16                 # model yaml over base
+    assert cfg['embedding_size'] == 48          # --config_file over yaml tree
+    assert cfg['n_layers'] == 3                 # command line over files
+    assert cfg['learning_rate'] == 0.25         # args dict over everything
+    assert cfg['scheduler'] == 'reduce'         # 'none' dropped
+    assert 'bogus_flag' not in cfg
+    assert cfg['cmd_args']['n_layers'] == 3
+
+
+def test_registry_resolves_reference_spelling():
+    for name in ('SASRec', 'GRU', 'AvgHist', 'SVDPlusPlus', 'MF'):
+        assert general.get_class_instance(name, 'unirec_b200/model').__name__ == name
+        assert general.get_class_instance(name, 'unirec/model').__name__ == name
+    with pytest.raises(ValueError):
+        general.get_class_instance('NoSuchModel', 'unirec_b200/model')
+
+
+def test_unsupported_options_fail_loudly():
+    g = Golden('mf_bpr')
+    with pytest.raises(ValueError):
+        build_model(g, loss_type='bce')
+    with pytest.raises(ValueError):
+        build_model(g, distance_type='cosine')
+
+
+def test_product_path_has_no_cpu_fallback():
+    g = Golden('mf_bpr')
+    model, _ = build_model(g)
+    model.train()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        model(**g.fwd_batch())
+
+
+def test_early_stopping_rule():
+    from unirec_b200.facility.trainer import Trainer
+    best, step, stop, upd = Trainer.early_stopping(0.5, None, 1, max_step=2)
+    assert (best, step, stop, upd) == (0.5, 0, False, True)
+    best, step, stop, upd = Trainer.early_stopping(0.4, best, step, max_step=2)
+    assert (best, step, stop, upd) == (0.5, 1, False, False)
+    best, step, stop, upd = Trainer.early_stopping(0.4, best, 2, max_step=2)
+    assert stop and not upd
+    assert Trainer.early_stopping(0.1, 0.9, 7, max_step=0) == (0.9, 7, False, True)
+
+
+def test_rank_metrics():
+    from unirec_b200.facility.evaluation import RankEvaluator
+    ev = RankEvaluator("['hit@1;3', 'ndcg@3', 'mrr', 'group_auc']")
+    res = ev.metrics_from_ranks(torch.tensor([0., 2., 5.], dtype=torch.float64), 11)
+    assert res['hit@1'] == pytest.approx(1 / 3) and res['hit@3'] == pytest.approx(2 / 3)
+    assert res['ndcg@3'] == pytest.approx((1.0 + 0.5) / 3)
+    assert res['mrr'] == pytest.approx((1 + 1 / 3 + 1 / 6) / 3)
+    assert res['group_auc'] == pytest.approx((1.0 + 0.8 + 0.5) / 3)

@@ -1,0 +1,26 @@
+// ABI glue: version query and the GEMM dispatcher (exact-fp32 SIMT kernel vs tcgen05 tensor-core kernel).
+#include "common.cuh"
+#include "../../include/unirec_b200.h"
+
+extern "C" int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                              int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp,
+                              int accumulate, int precision, void* stream) __attribute__((weak));
+
+extern "C" {
+
+int ur_version(void) { return UR_ABI_VERSION; }
+
+int ur_has_tensor_core_gemm(void) { return ur_gemm_tc_f32 != nullptr; }
+
+int ur_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate, int precision,
+                void* stream) {
+    if (precision != 0 && ur_gemm_tc_f32) {
+        const int rc = ur_gemm_tc_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, accumulate, precision,
+                                      stream);
+        if (rc != UR_ERR_UNSUPPORTED) return rc;     // shape not covered by the tensor-core kernel -> exact path
+    }
+    return ur_gemm_simt_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, accumulate, stream);
+}
+
+}  // extern "C"

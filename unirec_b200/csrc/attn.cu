@@ -1,0 +1,289 @@
+// K5: fused multi-head self-attention for short sequences (L <= 256), forward and backward.
+// Reference: unirec/model/modules.py:284-312 (scores / sqrt(d_h) + additive mask -> softmax -> P V) with the mask of
+// unirec/model/sequential/sasrec.py:40-57: 0 where the key is a real item (and key <= query when causal), else -10000.
+// The [B,H,L,L] score tensor never reaches HBM: K and V of one (sample, head) live in shared memory, one warp owns a
+// query row, softmax statistics by warp shuffles.  Backward recomputes P from the saved log-sum-exp.
+// Input layout: packed QKV [T, 3d] (row = q | k | v, head h at columns h*dh), output ctx [T, d].
+#include "common.cuh"
+
+namespace ur {
+
+constexpr float kMaskAdd = -10000.f;
+
+template <int DH>
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq, int L, int H,
+                                                       float scale, int causal, int q_tile, int q_only_last,
+                                                       float* __restrict__ ctx, float* __restrict__ lse) {
+    constexpr int KS = DH + 4;               // padded row stride: conflict-free float4 reads with lanes over keys
+    constexpr int CPL = (DH + 31) / 32;      // output columns per lane
+    extern __shared__ __align__(16) float smem[];
+    float* Ks = smem;                        // [L][KS]
+    float* Vs = Ks + (size_t)L * KS;         // [L][KS]
+    const int Lp = (L + 3) & ~3;             // keeps every sub-buffer 16-byte aligned
+    float* madd = Vs + (size_t)L * KS;       // [Lp]
+    float* pbuf = madd + Lp;                 // [8][Lp]
+    float* qbuf = pbuf + 8 * Lp;             // [8][DH]
+    const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+    const int d = H * DH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* base = qkv + (int64_t)b * L * 3 * d + h * DH;
+
+    for (int i = threadIdx.x; i < L * (DH / 4); i += blockDim.x) {
+        const int j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
+        *reinterpret_cast<float4*>(Ks + j * KS + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + d + c));
+        *reinterpret_cast<float4*>(Vs + j * KS + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + 2 * d + c));
+    }
+    for (int j = threadIdx.x; j < L; j += blockDim.x) madd[j] = seq[(int64_t)b * L + j] > 0 ? 0.f : kMaskAdd;
+    __syncthreads();
+
+    const int q_begin = q_only_last ? L - 1 : blockIdx.y * q_tile;
+    const int q_end = q_only_last ? L : min(L, q_begin + q_tile);
+    float* pw = pbuf + warp * Lp;
+    float* qw = qbuf + warp * DH;
+    for (int i = q_begin + warp; i < q_end; i += 8) {
+        for (int c = lane; c < DH; c += 32) qw[c] = __ldg(base + (int64_t)i * 3 * d + c);
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < L; j += 32) {
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4) {
+                const float4 q4 = *reinterpret_cast<const float4*>(qw + c);
+                const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * KS + c);
+                dot += f4_dot(q4, k4);
+            }
+            const float add = (causal && j > i) ? kMaskAdd : madd[j];
+            const float s = dot * scale + add;
+            pw[j] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < L; j += 32) {
+            const float p = __expf(pw[j] - mx);
+            pw[j] = p;
+            sum += p;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        float o[CPL];
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) o[r] = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float p = pw[j];
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                const int c = lane + 32 * r;
+                if (c < DH) o[r] = fmaf(p, Vs[j * KS + c], o[r]);
+            }
+        }
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            const int c = lane + 32 * r;
+            if (c < DH) ctx[((int64_t)b * L + i) * d + h * DH + c] = o[r] * inv;
+        }
+        if (lane == 0) lse[((int64_t)b * H + h) * L + i] = mx + __logf(sum);
+        __syncwarp();
+    }
+}
+
+// Backward: one CTA per (sample, head).  Query rows are processed in tiles of QT; phase A (warp per query row)
+// recomputes P, forms dS and writes dQ; phase B (warp per key, exclusive ownership -> no atomics) accumulates
+// dK and dV in registers across all tiles.
+template <int DH, int KPW>   // KPW = max keys owned per warp = ceil(L / 8)
+__global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq, int L, int H,
+                                                          float scale, int causal, int q_only_last, const float* __restrict__ ctx,
+                                                          const float* __restrict__ lse, const float* __restrict__ dctx,
+                                                          float* __restrict__ dqkv) {
+    constexpr int KS = DH + 4;
+    constexpr int CPL = (DH + 31) / 32;
+    constexpr int QT = 32;
+    extern __shared__ __align__(16) float smem[];
+    float* Ks = smem;                        // [L][KS]
+    float* Vs = Ks + (size_t)L * KS;         // [L][KS]
+    const int Lp = (L + 3) & ~3;
+    float* madd = Vs + (size_t)L * KS;       // [Lp]
+    float* Ps = madd + Lp;                   // [QT][Lp]
+    float* dSs = Ps + QT * Lp;               // [QT][Lp]  (already multiplied by scale)
+    float* Qs = dSs + QT * Lp;               // [QT][DH]
+    float* dOs = Qs + QT * DH;               // [QT][DH]
+    const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+    const int d = H * DH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* base = qkv + (int64_t)b * L * 3 * d + h * DH;
+    float* dbase = dqkv + (int64_t)b * L * 3 * d + h * DH;
+
+    for (int i = threadIdx.x; i < L * (DH / 4); i += blockDim.x) {
+        const int j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
+        *reinterpret_cast<float4*>(Ks + j * KS + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + d + c));
+        *reinterpret_cast<float4*>(Vs + j * KS + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + 2 * d + c));
+    }
+    for (int j = threadIdx.x; j < L; j += blockDim.x) madd[j] = seq[(int64_t)b * L + j] > 0 ? 0.f : kMaskAdd;
+
+    float dKr[KPW][CPL], dVr[KPW][CPL];
+#pragma unroll
+    for (int k = 0; k < KPW; ++k)
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { dKr[k][r] = 0.f; dVr[k][r] = 0.f; }
+
+    const int q_first = q_only_last ? L - 1 : 0;
+    for (int q0 = q_first; q0 < L; q0 += QT) {
+        const int nq = min(QT, L - q0);
+        __syncthreads();   // previous tile fully consumed (and K/V/madd visible on the first pass)
+        for (int i = threadIdx.x; i < nq * (DH / 4); i += blockDim.x) {
+            const int ii = i / (DH / 4), c = (i - ii * (DH / 4)) * 4;
+            const int64_t row = (int64_t)b * L + q0 + ii;
+            *reinterpret_cast<float4*>(Qs + ii * DH + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(q0 + ii) * 3 * d + c));
+            *reinterpret_cast<float4*>(dOs + ii * DH + c) = __ldg(reinterpret_cast<const float4*>(dctx + row * d + h * DH + c));
+        }
+        __syncthreads();
+        // ---- phase A ----
+        for (int ii = warp; ii < nq; ii += 8) {
+            const int i = q0 + ii;
+            const int64_t row = (int64_t)b * L + i;
+            float dsum = 0.f;
+            for (int c = lane; c < DH; c += 32) dsum = fmaf(dOs[ii * DH + c], __ldg(ctx + row * d + h * DH + c), dsum);
+            const float Di = warp_sum(dsum);
+            const float lse_i = lse[((int64_t)b * H + h) * L + i];
+            for (int j = lane; j < L; j += 32) {
+                float dot = 0.f, dp = 0.f;
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 q4 = *reinterpret_cast<const float4*>(Qs + ii * DH + c);
+                    const float4 g4 = *reinterpret_cast<const float4*>(dOs + ii * DH + c);
+                    const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * KS + c);
+                    const float4 v4 = *reinterpret_cast<const float4*>(Vs + j * KS + c);
+                    dot += f4_dot(q4, k4);
+                    dp += f4_dot(g4, v4);
+                }
+                const float add = (causal && j > i) ? kMaskAdd : madd[j];
+                const float p = __expf(dot * scale + add - lse_i);
+                Ps[ii * Lp + j] = p;
+                dSs[ii * Lp + j] = p * (dp - Di) * scale;
+            }
+            __syncwarp();
+            float dq[CPL];
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) dq[r] = 0.f;
+            for (int j = 0; j < L; ++j) {
+                const float ds = dSs[ii * Lp + j];
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) {
+                    const int c = lane + 32 * r;
+                    if (c < DH) dq[r] = fmaf(ds, Ks[j * KS + c], dq[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                const int c = lane + 32 * r;
+                if (c < DH) dbase[(int64_t)i * 3 * d + c] = dq[r];
+            }
+        }
+        __syncthreads();
+        // ---- phase B ----
+#pragma unroll
+        for (int k = 0; k < KPW; ++k) {
+            const int j = warp + 8 * k;
+            if (j < L) {
+                for (int ii = 0; ii < nq; ++ii) {
+                    const float ds = dSs[ii * Lp + j], p = Ps[ii * Lp + j];
+#pragma unroll
+                    for (int r = 0; r < CPL; ++r) {
+                        const int c = lane + 32 * r;
+                        if (c < DH) {
+                            dKr[k][r] = fmaf(ds, Qs[ii * DH + c], dKr[k][r]);
+                            dVr[k][r] = fmaf(p, dOs[ii * DH + c], dVr[k][r]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KPW; ++k) {
+        const int j = warp + 8 * k;
+        if (j < L) {
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                const int c = lane + 32 * r;
+                if (c < DH) {
+                    dbase[(int64_t)j * 3 * d + d + c] = dKr[k][r];
+                    dbase[(int64_t)j * 3 * d + 2 * d + c] = dVr[k][r];
+                }
+            }
+        }
+    }
+}
+
+static size_t attn_fwd_smem(int L, int dh) {
+    const size_t Lp = (L + 3) & ~3;
+    return sizeof(float) * ((size_t)2 * L * (dh + 4) + Lp + 8 * Lp + 8 * dh);
+}
+static size_t attn_bwd_smem(int L, int dh) {
+    const size_t Lp = (L + 3) & ~3;
+    return sizeof(float) * ((size_t)2 * L * (dh + 4) + Lp + 2 * 32 * Lp + 2 * 32 * dh);
+}
+
+}  // namespace ur
+
+extern "C" {
+
+// q_only_last: compute only query row L-1 (the last encoder layer feeds only [:, -1, :] into the scorer,
+// unirec/model/sequential/sasrec.py:74-75); all keys/values are still used.
+int ur_attn_fwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
+                    float* ctx, float* lse, void* stream) {
+    if (L <= 0 || L > 256 || H <= 0) return UR_ERR_BAD_ARG;
+    if (B == 0) return UR_OK;
+    const size_t smem = ur::attn_fwd_smem(L, dh);
+    if (smem > 220 * 1024) return UR_ERR_UNSUPPORTED;
+    const float scale = 1.f / sqrtf((float)dh);
+    const int q_tile = L <= 64 ? L : 64;
+    dim3 grid((unsigned)(B * H), q_only_last ? 1 : (L + q_tile - 1) / q_tile);
+    cudaStream_t st = (cudaStream_t)stream;
+#define UR_CASE(DH)                                                                                                    \
+    case DH:                                                                                                           \
+        if (smem > 48 * 1024)                                                                                          \
+            cudaFuncSetAttribute(ur::attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        ur::attn_fwd_kernel<DH><<<grid, 256, smem, st>>>(qkv, item_seq, L, H, scale, causal, q_tile, q_only_last, ctx, lse); \
+        break;
+    switch (dh) {
+        UR_CASE(16) UR_CASE(32) UR_CASE(64) UR_CASE(128)
+        default: return UR_ERR_UNSUPPORTED;
+    }
+#undef UR_CASE
+    UR_RETURN_LAST_ERROR();
+}
+
+// dqkv must be zero-filled by the caller when q_only_last (only row L-1 of dQ is written).
+int ur_attn_bwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
+                    const float* ctx, const float* lse, const float* dctx, float* dqkv, void* stream) {
+    if (L <= 0 || L > 256 || H <= 0) return UR_ERR_BAD_ARG;
+    if (B == 0) return UR_OK;
+    const size_t smem = ur::attn_bwd_smem(L, dh);
+    if (smem > 220 * 1024) return UR_ERR_UNSUPPORTED;
+    const float scale = 1.f / sqrtf((float)dh);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)(B * H);
+#define UR_LAUNCH(DH, KPW)                                                                                                  \
+    do {                                                                                                                    \
+        if (smem > 48 * 1024)                                                                                               \
+            cudaFuncSetAttribute(ur::attn_bwd_kernel<DH, KPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        ur::attn_bwd_kernel<DH, KPW><<<grid, 256, smem, st>>>(qkv, item_seq, L, H, scale, causal, q_only_last, ctx, lse, dctx, dqkv); \
+    } while (0)
+#define UR_CASE(DH)                                           \
+    case DH:                                                  \
+        if (L <= 64) UR_LAUNCH(DH, 8);                        \
+        else if (L <= 128) UR_LAUNCH(DH, 16);                 \
+        else UR_LAUNCH(DH, 32);                               \
+        break;
+    switch (dh) {
+        UR_CASE(16) UR_CASE(32) UR_CASE(64) UR_CASE(128)
+        default: return UR_ERR_UNSUPPORTED;
+    }
+#undef UR_CASE
+#undef UR_LAUNCH
+    UR_RETURN_LAST_ERROR();
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+// fp32 SIMT GEMM with fused epilogue (bias, activation, pre-activation stash, accumulate / split-K).
+// C[M,N] (+)= act(op(A)[M,K] * op(B)[K,N] + bias[N]);  row-major operands with leading dimensions.
+// This is the exact-fp32 path (parity bar 1e-3 is met with large margin); the tcgen05 tensor-core path for the
+// encoder's QKV/FFN GEMMs lives in gemm_tc.cu and is selected by ur_gemm_f32 when the shape qualifies.
+#include "common.cuh"
+
+namespace ur {
+
+constexpr int BM = 128, BN = 128, BK = 8;
+
+// Load a [BK x 128] k-major tile into shared memory from an operand that is either
+//   KCONTIG = true : stored [rows(=m or n), K], contiguous along k  -> float4 along k, transposed into smem
+//   KCONTIG = false: stored [K, rows],          contiguous along row -> float4 along the row dimension
+template <bool KCONTIG>
+__device__ __forceinline__ float4 tile_load(const float* __restrict__ P, int64_t ld, int row0, int nrows, int k0, int kend, int t) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KCONTIG) {
+        const int r = row0 + (t >> 1), k = k0 + (t & 1) * 4;
+        if (r < nrows && k < kend) v = __ldg(reinterpret_cast<const float4*>(P + (int64_t)r * ld + k));   // K % 4 == 0
+    } else {
+        const int k = k0 + (t >> 5), r = row0 + (t & 31) * 4;
+        if (k < kend && r < nrows) v = __ldg(reinterpret_cast<const float4*>(P + (int64_t)k * ld + r));   // rows % 4 == 0
+    }
+    return v;
+}
+template <bool KCONTIG>
+__device__ __forceinline__ void tile_store(float (*S)[BM], const float4& v, int t) {
+    if (KCONTIG) {
+        const int r = t >> 1, k = (t & 1) * 4;
+        S[k + 0][r] = v.x; S[k + 1][r] = v.y; S[k + 2][r] = v.z; S[k + 3][r] = v.w;
+    } else {
+        const int k = t >> 5, r = (t & 31) * 4;
+        *reinterpret_cast<float4*>(&S[k][r]) = v;
+    }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
+                                                        const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
+                                                        const float* __restrict__ bias, int act, float* __restrict__ preact,
+                                                        int64_t ldp, int accumulate, int k_chunk) {
+    __shared__ __align__(16) float As[2][BK][BM];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * k_chunk;
+    const int kend = min(K, kbeg + k_chunk);
+    const int tx = t & 15, ty = t >> 4;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // op(A)[m][k]: !TA -> A stored [M,K] (k contiguous); TA -> A stored [K,M] (m contiguous)
+    // op(B)[k][n]: !TB -> B stored [K,N] (n contiguous); TB -> B stored [N,K] (k contiguous)
+    float4 ra = tile_load<!TA>(A, lda, m0, M, kbeg, kend, t);
+    float4 rb = tile_load<TB>(B, ldb, n0, N, kbeg, kend, t);
+    tile_store<!TA>(As[0], ra, t);
+    tile_store<TB>(Bs[0], rb, t);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        const bool more = k0 + BK < kend;
+        if (more) {
+            ra = tile_load<!TA>(A, lda, m0, M, k0 + BK, kend, t);
+            rb = tile_load<TB>(B, ldb, n0, N, k0 + BK, kend, t);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) {
+            tile_store<!TA>(As[buf ^ 1], ra, t);
+            tile_store<TB>(Bs[buf ^ 1], rb, t);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+    const bool lead = blockIdx.z == 0;   // bias is added by the first K-split only
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            const int n = n0 + jh * 64 + tx * 4;
+            if (n >= N) continue;           // N % 4 == 0 -> whole float4 in or out
+            float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+            if (bias && lead) v = f4_add(v, __ldg(reinterpret_cast<const float4*>(bias + n)));
+            if (preact) *reinterpret_cast<float4*>(preact + (int64_t)m * ldp + n) = v;
+            if (act != ACT_NONE) {
+                v.x = act_fwd(v.x, act); v.y = act_fwd(v.y, act); v.z = act_fwd(v.z, act); v.w = act_fwd(v.w, act);
+            }
+            float* c = C + (int64_t)m * ldc + n;
+            if (accumulate == 1) red_add_v4(c, v);                      // split-K partials
+            else if (accumulate == 2) *reinterpret_cast<float4*>(c) = f4_add(*reinterpret_cast<float4*>(c), v);
+            else *reinterpret_cast<float4*>(c) = v;
+        }
+    }
+}
+
+// dX *= act'(preact)   (backward of the fused activation epilogue)
+__global__ void __launch_bounds__(256) act_bwd_kernel(float4* __restrict__ dY, const float4* __restrict__ pre, int64_t n4, int act) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g = dY[i];
+        const float4 x = pre[i];
+        g.x *= act_bwd(x.x, act); g.y *= act_bwd(x.y, act); g.z *= act_bwd(x.z, act); g.w *= act_bwd(x.w, act);
+        dY[i] = g;
+    }
+}
+
+// out[n] += sum_m X[m, n]   (bias gradients).  grid.x tiles columns by 128 (float4 x 32 lanes), grid.y splits rows.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int N, float* __restrict__ out) {
+    __shared__ float4 sh[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x * 128 + lane * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N)
+        for (int64_t m = (int64_t)blockIdx.y * 8 + warp; m < M; m += (int64_t)gridDim.y * 8)
+            s = f4_add(s, *reinterpret_cast<const float4*>(X + m * ldx + n));
+    sh[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && n < N) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s = f4_add(s, sh[w][lane]);
+        red_add_v4(out + n, s);
+    }
+}
+
+}  // namespace ur
+
+extern "C" {
+
+int ur_gemm_simt_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
+                     void* stream) {
+    if (M < 0 || N < 0 || K < 0 || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 3)) return UR_ERR_BAD_ARG;
+    if (!transA && (K & 3)) return UR_ERR_BAD_ARG;      // A contiguous along k
+    if (transA && (M & 3)) return UR_ERR_BAD_ARG;       // A contiguous along m
+    if (transB && (K & 3)) return UR_ERR_BAD_ARG;       // B contiguous along k
+    if (preact && (ldp & 3)) return UR_ERR_BAD_ARG;
+    if (M == 0 || N == 0) return UR_OK;
+    const int gx = (int)((N + ur::BN - 1) / ur::BN), gy = (int)((M + ur::BM - 1) / ur::BM);
+    int splits = 1;
+    int64_t k_chunk = K;
+    if (accumulate && !preact && act == 0) {            // split-K only where the epilogue is linear
+        const int64_t tiles = (int64_t)gx * gy;
+        const int64_t want = (2 * ur::kNumSMs + tiles - 1) / tiles;
+        const int64_t maxs = (K + 255) / 256;
+        splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
+        if (splits < 1) splits = 1;
+        k_chunk = ((K + splits - 1) / splits + ur::BK - 1) / ur::BK * ur::BK;
+        splits = (int)((K + k_chunk - 1) / k_chunk);
+        if (splits < 1) { splits = 1; k_chunk = ur::BK; }
+    }
+    if (accumulate) accumulate = splits > 1 ? 1 : 2;    // atomics only when several CTAs share an output tile
+    dim3 grid(gx, gy, splits);
+    cudaStream_t st = (cudaStream_t)stream;
+#define UR_GEMM(TA, TB)                                                                                                   \
+    ur::gemm_simt_kernel<TA, TB><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, \
+                                                       accumulate, (int)k_chunk)
+    if (!transA && !transB) UR_GEMM(false, false);
+    else if (!transA && transB) UR_GEMM(false, true);
+    else if (transA && !transB) UR_GEMM(true, false);
+    else UR_GEMM(true, true);
+#undef UR_GEMM
+    UR_RETURN_LAST_ERROR();
+}
+
+int ur_act_bwd_f32(float* dY, const float* preact, int64_t n, int act, void* stream) {
+    if (n & 3) return UR_ERR_BAD_ARG;
+    if (n == 0 || act == 0) return UR_OK;
+    int64_t blocks = (n / 4 + 255) / 256;
+    const int64_t cap = (int64_t)ur::kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    ur::act_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float4*)dY, (const float4*)preact, n / 4, act);
+    UR_RETURN_LAST_ERROR();
+}
+
+int ur_colsum_accum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* stream) {
+    if ((N & 3) || (ldx & 3)) return UR_ERR_BAD_ARG;
+    if (M == 0 || N == 0) return UR_OK;
+    int gy = (int)((M + 255) / 256);
+    if (gy > 256) gy = 256;
+    if (gy < 1) gy = 1;
+    dim3 grid((unsigned)((N + 127) / 128), gy);
+    ur::colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, M, (int)N, out);
+    UR_RETURN_LAST_ERROR();
+}
+
+}  // extern "C"

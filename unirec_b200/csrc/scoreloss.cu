@@ -1,0 +1,367 @@
+// K8: fused target/negative gather -> inner-product scores -> bias / tau / clamp -> sampled-softmax or BPR loss
+//     -> dLoss/dscore and dLoss/du, in ONE pass over the table rows.  The [B,1+K,d] tensor of the reference
+//     (unirec/model/base/recommender.py:55,66-67) is never materialised: every row is read from HBM exactly once.
+//
+// Reference arithmetic restated here:
+//   scores  : unirec/model/modules.py:59-66 (InnerProductScorer), recommender.py:76-96 (bias, /tau, clamp)
+//   softmax : unirec/model/base/reco_abc.py:260-265   loss = mean over {label>0} of (logsumexp_j s_bj - s_bj)
+//   bpr     : reco_abc.py:252-255, modules.py:15-21   loss = mean_{b,j>=1} -log(1e-8 + sigmoid(s_b0 - s_bj))
+//
+// The softmax branch is a single-query attention: an online (max, sum, weighted-row-sum) recurrence gives
+// dL/du = (n_b * sum_j p_j m_j e_j - sum_j y_j m_j e_j) / (P tau) without a second pass over the rows
+// (m_j = clamp pass-through mask, n_b = positives in row b, P = positives in the batch).
+#include "common.cuh"
+
+namespace ur {
+
+struct ScoreLossParams {
+    const float4* table;      // [V, d]
+    const float4* user_emb;   // [B, d]
+    const int64_t* item_id;   // [B, N]
+    const int32_t* label;     // [B, N] or null (column 0 positive)
+    const float* item_bias;   // [V] or null
+    const float* user_bias;   // [n_users] or null
+    const int64_t* user_id;   // [B] (only with user_bias)
+    const float* norm_dev;    // device scalar normaliser (softmax: P) or null -> norm_host
+    float norm_host;
+    float inv_tau, clip;      // clip <= 0: no clamp
+    int N;
+    int64_t B;
+    int wps;                  // warps per sample (1,2,4,8)
+    float* scores;            // [B, N] final scores (may be null)
+    float* loss_vec;          // [B]
+    float* dscore;            // [B, N] dLoss/d(dot)   (may be null -> forward only)
+    float4* grad_user;        // [B, d]                (may be null -> forward only)
+};
+
+constexpr float kBprEps = 1e-8f;   // unirec/constants/global_variables.py:4
+
+template <int D4, int LOSS>   // LOSS 0 = softmax, 1 = bpr
+__global__ void __launch_bounds__(256) score_loss_kernel(const ScoreLossParams p) {
+    constexpr int LPR = D4 < 32 ? D4 : 32;   // lanes per row
+    constexpr int VPL = D4 / LPR;            // float4 per lane
+    constexpr int RPW = 32 / LPR;            // row groups per warp
+    constexpr int D = D4 * 4;
+    constexpr int U = 4;                     // rows in flight per group
+    extern __shared__ float smem[];
+
+    const int wps = p.wps, spb = 8 / wps, G = wps * RPW, N = p.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ls = warp / wps;                       // local sample
+    const int wis = warp - ls * wps;                 // warp in sample
+    const int sub = lane / LPR, col = lane % LPR;
+    const int g = wis * RPW + sub;                   // group in sample
+    const int64_t b = (int64_t)blockIdx.x * spb + ls;
+    const bool live = b < p.B;
+
+    // shared layout
+    float* zbuf = smem;                                  // [spb][N]      scaled, unclamped scores
+    float* gstate = zbuf + (size_t)spb * N;              // [spb][G][4]
+    float* gacc = gstate + spb * G * 4;                  // [spb][G][D]
+    float* aux = gacc + (size_t)spb * G * D;             // [spb][D]      softmax: sum_j y_j m_j e_j ; bpr: e_0
+
+    for (int i = threadIdx.x; i < spb * D; i += blockDim.x) aux[i] = 0.f;
+    __syncthreads();
+
+    float4 uvec[VPL];
+    float ub = 0.f;
+    const int64_t* ids = p.item_id + (live ? b : 0) * N;
+    const int32_t* lab = p.label ? p.label + (live ? b : 0) * N : nullptr;
+    if (live) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) uvec[v] = __ldg(p.user_emb + b * D4 + v * LPR + col);
+        if (p.user_bias) ub = __ldg(p.user_bias + __ldg(p.user_id + b));
+    }
+    const float clip = p.clip;
+    const bool has_clip = clip > 0.f;
+
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float st_m = -INFINITY, st_l = 0.f;   // softmax: running max / sum.    bpr: st_l = sum_j loss_j
+    float st_a = 0.f, st_b = 0.f;         // softmax: sum y_j s_j, sum y_j. bpr: st_a = sum_j c_j
+    float s0 = 0.f, mask0 = 1.f;
+    float4 e0[VPL];
+
+    if (LOSS == 1 && live) {               // BPR needs s_0 before any negative: every group reads row 0 (L2 hit)
+        const int64_t id0 = __ldg(ids);
+        float dot = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            e0[v] = ldg_stream(p.table + id0 * D4 + v * LPR + col);
+            dot += f4_dot(e0[v], uvec[v]);
+        }
+        dot = group_sum<LPR>(dot);
+        float z = (dot + ub + (p.item_bias ? __ldg(p.item_bias + id0) : 0.f)) * p.inv_tau;
+        s0 = has_clip ? fminf(fmaxf(z, -clip), clip) : z;
+        mask0 = (has_clip && (z < -clip || z > clip)) ? 0.f : 1.f;
+        if (g == 0) {
+            if (col == 0) zbuf[(size_t)ls * N] = z;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                reinterpret_cast<float4*>(aux + ls * D)[v * LPR + col] = e0[v];
+        }
+    }
+
+    if (live) {
+        const int jstart = LOSS == 1 ? 1 : 0;
+        for (int j0 = jstart + g; j0 < N; j0 += G * U) {
+            float4 row[U][VPL];
+            float bias[U];
+            int32_t y[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + u * G;
+                bias[u] = 0.f; y[u] = 0;
+                if (j < N) {
+                    const int64_t id = __ldg(ids + j);
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) row[u][v] = ldg_stream(p.table + id * D4 + v * LPR + col);
+                    if (p.item_bias) bias[u] = __ldg(p.item_bias + id);
+                    if (LOSS == 0) y[u] = lab ? __ldg(lab + j) : (j == 0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + u * G;
+                if (j < N) {
+                    float dot = 0.f;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) dot += f4_dot(row[u][v], uvec[v]);
+                    dot = group_sum<LPR>(dot);
+                    const float z = (dot + ub + bias[u]) * p.inv_tau;
+                    const float s = has_clip ? fminf(fmaxf(z, -clip), clip) : z;
+                    const float mask = (has_clip && (z < -clip || z > clip)) ? 0.f : 1.f;
+                    if (col == 0) zbuf[(size_t)ls * N + j] = z;
+                    if (LOSS == 0) {
+                        if (s > st_m) {
+                            const float sc = __expf(st_m - s);
+                            st_l *= sc;
+#pragma unroll
+                            for (int v = 0; v < VPL; ++v) acc[v] = f4_scale(acc[v], sc);
+                            st_m = s;
+                        }
+                        const float pj = __expf(s - st_m);
+                        st_l += pj;
+                        const float w = pj * mask;
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(w, row[u][v], acc[v]);
+                        if (y[u] > 0) {
+                            st_a += s; st_b += 1.f;
+                            if (mask != 0.f) {
+#pragma unroll
+                                for (int v = 0; v < VPL; ++v) {
+                                    float* a = aux + ls * D + (v * LPR + col) * 4;
+                                    atomicAdd(a + 0, row[u][v].x); atomicAdd(a + 1, row[u][v].y);
+                                    atomicAdd(a + 2, row[u][v].z); atomicAdd(a + 3, row[u][v].w);
+                                }
+                            }
+                        }
+                    } else {
+                        const float x = s0 - s;
+                        const float sig = 1.f / (1.f + __expf(-x));
+                        st_l += -__logf(kBprEps + sig);
+                        const float c = sig * (1.f - sig) / (kBprEps + sig);
+                        st_a += c;
+                        const float w = c * mask;
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(w, row[u][v], acc[v]);
+                    }
+                }
+            }
+        }
+        // publish group state
+        if (col == 0) {
+            float* gs = gstate + (ls * G + g) * 4;
+            gs[0] = st_m; gs[1] = st_l; gs[2] = st_a; gs[3] = st_b;
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            reinterpret_cast<float4*>(gacc + (size_t)(ls * G + g) * D)[v * LPR + col] = acc[v];
+    }
+    __syncthreads();
+
+    // ---- combine the G groups of each sample; threads of the sample's warps cooperate ----
+    const int tis = wis * 32 + lane;          // thread in sample
+    const int tps = wps * 32;                 // threads per sample
+    float norm = p.norm_dev ? __ldg(p.norm_dev) : p.norm_host;
+    if (live) {
+        float m_all = -INFINITY;
+        if (LOSS == 0)
+            for (int q = 0; q < G; ++q) m_all = fmaxf(m_all, gstate[(ls * G + q) * 4]);
+        float l_all = 0.f, a_all = 0.f, b_all = 0.f;
+        for (int q = 0; q < G; ++q) {
+            const float* gs = gstate + (ls * G + q) * 4;
+            if (LOSS == 0) {
+                const float sc = gs[1] > 0.f ? __expf(gs[0] - m_all) : 0.f;
+                l_all += gs[1] * sc;
+            } else {
+                l_all += gs[1];
+            }
+            a_all += gs[2]; b_all += gs[3];
+        }
+        if (LOSS == 0) {
+            const float lse = m_all + __logf(l_all);
+            const float gscale = p.inv_tau / norm;
+            if (p.grad_user) {
+                for (int c = tis; c < D; c += tps) {
+                    float a = 0.f;
+                    for (int q = 0; q < G; ++q) {
+                        const float* gs = gstate + (ls * G + q) * 4;
+                        const float sc = gs[1] > 0.f ? __expf(gs[0] - m_all) : 0.f;
+                        a += gacc[(size_t)(ls * G + q) * D + c] * sc;
+                    }
+                    reinterpret_cast<float*>(p.grad_user)[b * D + c] = (b_all * a / l_all - aux[ls * D + c]) * gscale;
+                }
+            }
+            if (tis == 0) p.loss_vec[b] = b_all * lse - a_all;
+            for (int j = tis; j < N; j += tps) {
+                const float z = zbuf[(size_t)ls * N + j];
+                const float s = has_clip ? fminf(fmaxf(z, -clip), clip) : z;
+                if (p.scores) p.scores[b * N + j] = s;
+                if (p.dscore) {
+                    const float mask = (has_clip && (z < -clip || z > clip)) ? 0.f : 1.f;
+                    const float yj = lab ? (float)(__ldg(lab + j) > 0) : (float)(j == 0);
+                    p.dscore[b * N + j] = (b_all * __expf(s - lse) - yj) * mask * gscale;
+                }
+            }
+        } else {
+            const float K = (float)(N - 1);
+            const float gscale = p.inv_tau / norm;        // norm = B*K
+            if (p.grad_user) {
+                for (int c = tis; c < D; c += tps) {
+                    float a = 0.f;
+                    for (int q = 0; q < G; ++q) a += gacc[(size_t)(ls * G + q) * D + c];
+                    reinterpret_cast<float*>(p.grad_user)[b * D + c] = (a - a_all * mask0 * aux[ls * D + c]) * gscale;
+                }
+            }
+            if (tis == 0) p.loss_vec[b] = l_all / K;
+            for (int j = tis; j < N; j += tps) {
+                const float z = zbuf[(size_t)ls * N + j];
+                const float s = has_clip ? fminf(fmaxf(z, -clip), clip) : z;
+                if (p.scores) p.scores[b * N + j] = s;
+                if (p.dscore) {
+                    float gj;
+                    if (j == 0) {
+                        gj = -a_all * mask0 * gscale;
+                    } else {
+                        const float mask = (has_clip && (z < -clip || z > clip)) ? 0.f : 1.f;
+                        const float x = s0 - s;
+                        const float sig = 1.f / (1.f + __expf(-x));
+                        gj = sig * (1.f - sig) / (kBprEps + sig) * mask * gscale;
+                    }
+                    p.dscore[b * N + j] = gj;
+                }
+            }
+        }
+    }
+}
+
+// loss = sum(loss_vec) / denom   (denom from device when given); NaN flag for the trainer's skip-step rule
+// (unirec/facility/trainer.py:164-168, 344-352) without a host sync in the step.
+__global__ void __launch_bounds__(1024) loss_finish_kernel(const float* __restrict__ loss_vec, int64_t B, const float* denom_dev,
+                                                           float denom_host, float* __restrict__ loss_out, int32_t* nan_flag) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) s += (double)loss_vec[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) {
+            const float denom = denom_dev ? *denom_dev : denom_host;
+            const float loss = (float)(s / (double)denom);
+            *loss_out = loss;
+            if (nan_flag) *nan_flag = isnan(loss) ? 1 : 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) count_positive_kernel(const int32_t* __restrict__ label, int64_t n, float* out) {
+    // single CTA; labels are tiny next to the table rows
+    __shared__ int sh[8];
+    int c = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) c += label[i] > 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += sh[i];
+        *out = (float)t;
+    }
+}
+
+static size_t score_loss_smem(int d, int N, int wps) {
+    const int d4 = d / 4, lpr = d4 < 32 ? d4 : 32, rpw = 32 / lpr;
+    const int spb = 8 / wps, G = wps * rpw;
+    return sizeof(float) * ((size_t)spb * N + (size_t)spb * G * 4 + (size_t)spb * G * d + (size_t)spb * d);
+}
+
+template <int D4>
+static int launch_score_loss(const ScoreLossParams& p, int loss_type, size_t smem, cudaStream_t st) {
+    const int spb = 8 / p.wps;
+    const unsigned grid = (unsigned)((p.B + spb - 1) / spb);
+    if (loss_type == 0) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(score_loss_kernel<D4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        score_loss_kernel<D4, 0><<<grid, 256, smem, st>>>(p);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(score_loss_kernel<D4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        score_loss_kernel<D4, 1><<<grid, 256, smem, st>>>(p);
+    }
+    return 0;
+}
+
+}  // namespace ur
+
+extern "C" {
+
+int ur_count_positive_i32(const int32_t* label, int64_t n, float* out, void* stream) {
+    ur::count_positive_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(label, n, out);
+    UR_RETURN_LAST_ERROR();
+}
+
+int ur_loss_finish_f32(const float* loss_vec, int64_t B, const float* denom_dev, float denom_host, float* loss_out,
+                       int32_t* nan_flag, void* stream) {
+    ur::loss_finish_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(loss_vec, B, denom_dev, denom_host, loss_out, nan_flag);
+    UR_RETURN_LAST_ERROR();
+}
+
+int ur_score_loss_fwd_bwd_f32(const float* table, int d, const float* user_emb, const int64_t* item_id, int64_t B, int N,
+                              const int32_t* label, const float* item_bias, const float* user_bias, const int64_t* user_id,
+                              float tau, float score_clip, int loss_type, const float* norm_dev, float norm_host, float* scores,
+                              float* loss_vec, float* dscore, float* grad_user, void* stream) {
+    if (d <= 0 || (d & 3) || N <= 0 || (loss_type != 0 && loss_type != 1) || tau == 0.f) return UR_ERR_BAD_ARG;
+    if (loss_type == 1 && N < 2) return UR_ERR_BAD_ARG;
+    if (B == 0) return UR_OK;
+    ur::ScoreLossParams p;
+    p.table = (const float4*)table; p.user_emb = (const float4*)user_emb; p.item_id = item_id; p.label = label;
+    p.item_bias = item_bias; p.user_bias = user_bias; p.user_id = user_id; p.norm_dev = norm_dev; p.norm_host = norm_host;
+    p.inv_tau = 1.f / tau; p.clip = score_clip; p.N = N; p.B = B;
+    p.scores = scores; p.loss_vec = loss_vec; p.dscore = dscore; p.grad_user = (float4*)grad_user;
+    const int rpw = d >= 128 ? 1 : 128 / d;
+    int wps = 1;
+    while (wps < 8 && N > wps * rpw * 8) wps *= 2;     // >= 8 rows per group before adding warps
+    size_t smem = ur::score_loss_smem(d, N, wps);
+    while (smem > 200 * 1024 && wps < 8) { wps *= 2; smem = ur::score_loss_smem(d, N, wps); }
+    if (smem > 200 * 1024) return UR_ERR_UNSUPPORTED;
+    p.wps = wps;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d) {
+        case 16: ur::launch_score_loss<4>(p, loss_type, smem, st); break;
+        case 32: ur::launch_score_loss<8>(p, loss_type, smem, st); break;
+        case 64: ur::launch_score_loss<16>(p, loss_type, smem, st); break;
+        case 128: ur::launch_score_loss<32>(p, loss_type, smem, st); break;
+        case 256: ur::launch_score_loss<64>(p, loss_type, smem, st); break;
+        case 512: ur::launch_score_loss<128>(p, loss_type, smem, st); break;
+        default: return UR_ERR_UNSUPPORTED;
+    }
+    UR_RETURN_LAST_ERROR();
+}
+
+}  // extern "C"

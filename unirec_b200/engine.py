@@ -1,0 +1,520 @@
+"""Host-side execution engine of the hot path: explicit forward/backward over the CUDA kernels.
+
+One engine per model instance.  It owns
+  * the flat fp32 buffer holding every dense (non-table) parameter and the matching flat gradient buffer
+    (nn.Parameters are re-pointed into it, state_dict names unchanged -> one optimizer launch, one all-reduce);
+  * the activation workspace (allocated once per batch shape, reused every step);
+  * per-table row-list state (head/next/uniq) that carries the sparse embedding gradient to the optimizer without
+    ever materialising a [V,d] gradient.
+
+Reference call stack being replaced: BaseRecommender.forward -> forward_item_emb / forward_user_emb / _predict_layer /
+_cal_loss (unirec/model/base/recommender.py:46-96, reco_abc.py:220-272) and its autograd.
+"""
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+PRECISION_CODES = {'fp32': 0, 'tf32': 1, 'bf16': 2}
+
+
+class Workspace:
+    """Named device buffers, reallocated only when a shape changes (static shapes -> CUDA-graph friendly)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf: Dict[str, torch.Tensor] = {}
+
+    def get(self, name, shape, dtype=torch.float32, zero=False):
+        shape = tuple(int(s) for s in shape)
+        t = self.buf.get(name)
+        if t is None or t.shape != shape or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.buf[name] = t
+        if zero:
+            t.zero_()
+        return t
+
+
+class FlatParams:
+    """Packs dense parameters into one contiguous fp32 buffer (each slot 16-byte aligned) and re-points
+    `param.data` into it.  `groups` lists parameter names that must be adjacent (e.g. query/key/value weights
+    -> one [3d,d] matrix)."""
+
+    def __init__(self, named_params: List, device):
+        self.names = [n for n, _ in named_params]
+        self.offsets, total = {}, 0
+        for n, p in named_params:
+            self.offsets[n] = (total, p.numel(), tuple(p.shape))
+            total += (p.numel() + 3) // 4 * 4
+        self.size = total
+        self.data = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=device)
+        for n, p in named_params:
+            off, cnt, shape = self.offsets[n]
+            view = self.data[off:off + cnt].view(shape)
+            view.copy_(p.data.to(device))
+            p.data = view
+
+    def p(self, name):
+        off, cnt, shape = self.offsets[name]
+        return self.data[off:off + cnt].view(shape)
+
+    def g(self, name):
+        off, cnt, shape = self.offsets[name]
+        return self.grad[off:off + cnt].view(shape)
+
+    def span(self, first, last):
+        """Contiguous view covering parameters first..last (adjacent in the buffer), as a flat tensor."""
+        o0 = self.offsets[first][0]
+        o1, c1, _ = self.offsets[last]
+        return self.data[o0:o1 + c1], self.grad[o0:o1 + c1]
+
+
+class RowGrad:
+    """Sparse gradient of one table for one step: which batch entries touch which rows, and where the per-entry
+    gradient rows live.  Consumed by FusedOptimizer through ur_rowlist_link / ur_rowlist_apply."""
+
+    def __init__(self, param: torch.nn.Parameter):
+        self.param = param
+        self.head = None           # int32 [V], -1 between steps
+        self.next = None
+        self.uniq = None
+        self.n_uniq = None
+        self.specs = []            # list of (keys, src, src_group, coef, coef_group)
+        self.linked = False
+
+    def reset(self):
+        self.specs = []
+        self.linked = False
+
+    def add(self, keys, src, src_group=1, coef=None, coef_group=1):
+        if len(self.specs) >= 2:
+            raise RuntimeError('a table takes at most two gradient sources per step')
+        self.specs.append((keys, src, int(src_group), coef, int(coef_group)))
+
+    def n_entries(self):
+        return sum(k.numel() for k, *_ in self.specs)
+
+    def link(self):
+        """Thread the batch entries onto per-row lists (idempotent within a step)."""
+        if self.linked or not self.specs:
+            return
+        dev = self.param.device
+        V = self.param.shape[0]
+        n = self.n_entries()
+        if self.head is None or self.head.numel() != V:
+            self.head = torch.full((V,), -1, dtype=torch.int32, device=dev)
+        if self.next is None or self.next.numel() < n:
+            self.next = torch.empty(n, dtype=torch.int32, device=dev)
+            self.uniq = torch.empty(n, dtype=torch.int32, device=dev)
+        if self.n_uniq is None:
+            self.n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.n_uniq.zero_()
+        off = 0
+        for keys, *_ in self.specs:
+            ops.rowlist_link(self.head, keys, off, self.next, self.uniq, self.n_uniq, pad_id=0)
+            off += keys.numel()
+        self.linked = True
+
+    def sources(self):
+        return [(src, sg, coef, cg, keys.numel()) for keys, src, sg, coef, cg in self.specs]
+
+    def to_dense(self):
+        """Exact-dense mode: materialise the [V,d] gradient the reference's autograd would produce."""
+        g = torch.zeros_like(self.param.data)
+        for keys, src, sg, coef, cg in self.specs:
+            ops.scatter_add_rows(g, keys, src, sg, coef, cg, pad_id=0)
+        return g
+
+
+def _lin_fwd(x, M, K, w, b, N, out, act=None, preact=None, lda=None, prec=0):
+    """out[M,N] = act(x[M,K] @ w[N,K]^T + b)"""
+    return ops.gemm(x, w, out, M, N, K, transB=True, lda=lda, bias=b, act=act, preact=preact, precision=prec)
+
+
+def _lin_bwd(dy, M, N, x, K, w, dx, dw, db, lda_x=None, accumulate_dx=False, prec=0, lddy=None, lddx=None):
+    """y = x w^T + b.  dx[M,K] (+)= dy[M,N] @ w[N,K];  dw[N,K] += dy^T x;  db[N] += colsum(dy)."""
+    if dx is not None:
+        ops.gemm(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec)
+    ops.gemm(dy, x, dw, N, K, M, transA=True, lda=lddy or N, ldb=lda_x, accumulate=True, precision=prec)
+    if db is not None:
+        ops.colsum_accum(dy, M, N, db, ldx=lddy)
+
+
+# ==================================================================================================
+# Towers: forward(batch) -> user_emb [B,d];  backward(d_user_emb) -> dense grads into FlatParams.grad, row grads
+# registered on the tables' RowGrad.
+# ==================================================================================================
+class SASRecTower:
+    """unirec/model/sequential/sasrec.py:59-76 over modules.TransformerEncoder (modules.py:247-433)."""
+
+    def __init__(self, eng, cfg):
+        self.eng = eng
+        self.d = int(cfg['embedding_size'])
+        self.n_layers = int(cfg['n_layers'])
+        self.H = int(cfg['n_heads'])
+        self.I = int(cfg['inner_size'])
+        self.act = cfg['hidden_act']
+        self.eps = float(cfg['layer_norm_eps'])
+        self.causal = bool(cfg['use_position_emb'])
+        self.dh = self.d // self.H
+
+    @staticmethod
+    def flat_order(model):
+        names = []
+        if model.position_embedding is not None:
+            names.append('position_embedding.weight')
+        names += ['LayerNorm.weight', 'LayerNorm.bias']
+        for i in range(model.n_layers):
+            a, f = 'trm_encoder.layer.%d.multi_head_attention.' % i, 'trm_encoder.layer.%d.feed_forward.' % i
+            names += [a + 'query.weight', a + 'key.weight', a + 'value.weight',
+                      a + 'query.bias', a + 'key.bias', a + 'value.bias',
+                      a + 'dense.weight', a + 'dense.bias', a + 'LayerNorm.weight', a + 'LayerNorm.bias',
+                      f + 'dense_1.weight', f + 'dense_1.bias', f + 'dense_2.weight', f + 'dense_2.bias',
+                      f + 'LayerNorm.weight', f + 'LayerNorm.bias']
+        return names
+
+    def forward(self, item_seq, save=True, **_):
+        eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
+        B, L = item_seq.shape
+        d, I, H, T, prec = self.d, self.I, self.H, B * L, eng.prec
+        table = eng.table_for_seq().data
+        pos = fp.p('position_embedding.weight') if self.causal else None
+        x = ws.get('x0', (T, d))
+        self.mean0, self.rstd0 = ws.get('mean0', (T,)), ws.get('rstd0', (T,))
+        ops.seq_prep_ln_fwd(table, pos, fp.p('LayerNorm.weight'), fp.p('LayerNorm.bias'), self.eps, item_seq, x,
+                            self.mean0, self.rstd0)
+        self.saved = []
+        for i in range(self.n_layers):
+            a, f = 'trm_encoder.layer.%d.multi_head_attention.' % i, 'trm_encoder.layer.%d.feed_forward.' % i
+            tag = str(i) if save else 'e'
+            wqkv, _ = fp.span(a + 'query.weight', a + 'value.weight')
+            bqkv, _ = fp.span(a + 'query.bias', a + 'value.bias')
+            qkv = ws.get('qkv' + tag, (T, 3 * d))
+            _lin_fwd(x, T, d, wqkv, bqkv, 3 * d, qkv, prec=prec)
+            ctx, lse = ws.get('ctx' + tag, (T, d)), ws.get('lse' + tag, (B, H, L))
+            ops.attn_fwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse)
+            z1 = ws.get('z1' + tag, (T, d))
+            _lin_fwd(ctx, T, d, fp.p(a + 'dense.weight'), fp.p(a + 'dense.bias'), d, z1, prec=prec)
+            x1 = ws.get('x1' + tag, (T, d))
+            m1, r1 = ws.get('m1' + tag, (T,)), ws.get('r1' + tag, (T,))
+            ops.add_ln_fwd(z1, x, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1)
+            hpre, hact = ws.get('hpre' + tag, (T, I)), ws.get('hact' + tag, (T, I))
+            _lin_fwd(x1, T, d, fp.p(f + 'dense_1.weight'), fp.p(f + 'dense_1.bias'), I, hact, act=self.act, preact=hpre,
+                     prec=prec)
+            z2 = ws.get('z2' + tag, (T, d))
+            _lin_fwd(hact, T, I, fp.p(f + 'dense_2.weight'), fp.p(f + 'dense_2.bias'), d, z2, prec=prec)
+            x2 = ws.get('x2' + tag, (T, d))
+            m2, r2 = ws.get('m2' + tag, (T,)), ws.get('r2' + tag, (T,))
+            ops.add_ln_fwd(z2, x1, fp.p(f + 'LayerNorm.weight'), fp.p(f + 'LayerNorm.bias'), self.eps, x2, m2, r2)
+            if save:
+                self.saved.append((x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2))
+            x = x2
+        self.item_seq = item_seq
+        user = ws.get('user_emb', (B, d))
+        user.copy_(x.view(B, L, d)[:, L - 1, :])
+        return user
+
+    def backward(self, d_user):
+        eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
+        item_seq = self.item_seq
+        B, L = item_seq.shape
+        d, I, H, T, prec = self.d, self.I, self.H, B * L, eng.prec
+        dx = ws.get('dx_a', (T, d), zero=True)
+        dx.view(B, L, d)[:, L - 1, :] = d_user
+        for i in reversed(range(self.n_layers)):
+            a, f = 'trm_encoder.layer.%d.multi_head_attention.' % i, 'trm_encoder.layer.%d.feed_forward.' % i
+            x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2 = self.saved[i]
+            # x2 = LN(z2), z2 = ffn(x1) + x1
+            dz2 = ws.get('dz2', (T, d))
+            ops.add_ln_bwd(z2, fp.p(f + 'LayerNorm.weight'), m2, r2, dx, dz2, fp.g(f + 'LayerNorm.weight'),
+                           fp.g(f + 'LayerNorm.bias'))
+            dh = ws.get('dh', (T, I))
+            _lin_bwd(dz2, T, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'),
+                     fp.g(f + 'dense_2.bias'), prec=prec)
+            ops.act_bwd(dh, hpre, self.act)
+            # dx1 = dz2 (residual) + dh @ W1   -> accumulate into dz2
+            _lin_bwd(dh, T, I, x1, d, fp.p(f + 'dense_1.weight'), dz2, fp.g(f + 'dense_1.weight'),
+                     fp.g(f + 'dense_1.bias'), accumulate_dx=True, prec=prec)
+            # x1 = LN(z1), z1 = attn_out + x
+            dz1 = ws.get('dz1_%d' % (i % 2), (T, d))     # becomes this layer's input gradient (no copy)
+            ops.add_ln_bwd(z1, fp.p(a + 'LayerNorm.weight'), m1, r1, dz2, dz1, fp.g(a + 'LayerNorm.weight'),
+                           fp.g(a + 'LayerNorm.bias'))
+            dctx = ws.get('dctx', (T, d))
+            _lin_bwd(dz1, T, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), fp.g(a + 'dense.bias'),
+                     prec=prec)
+            dqkv = ws.get('dqkv', (T, 3 * d))
+            ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv)
+            wqkv, gwqkv = fp.span(a + 'query.weight', a + 'value.weight')
+            _, gbqkv = fp.span(a + 'query.bias', a + 'value.bias')
+            # dx = dz1 (residual) + dqkv @ Wqkv  -> accumulate into dz1
+            _lin_bwd(dqkv, T, 3 * d, x, d, wqkv, dz1, gwqkv, gbqkv, accumulate_dx=True, prec=prec)
+            dx = dz1
+        table = eng.table_for_seq()
+        pos = fp.p('position_embedding.weight') if self.causal else None
+        drows = ws.get('drows', (T, d))
+        ops.seq_prep_ln_bwd(table.data, pos, fp.p('LayerNorm.weight'), item_seq, self.mean0, self.rstd0, dx, drows,
+                            fp.g('LayerNorm.weight'), fp.g('LayerNorm.bias'),
+                            fp.g('position_embedding.weight') if self.causal else None)
+        eng.rowgrad(table).add(item_seq, drows, 1, None, 1)
+
+
+class GRUTower:
+    """unirec/model/sequential/gru.py:27-35.  `dense` is applied to the last step only (the other L-1 outputs of
+    the reference's all-steps Linear are dead)."""
+
+    def __init__(self, eng, cfg):
+        self.eng = eng
+        self.d = int(cfg['embedding_size'])
+        self.Hd = int(cfg.get('hidden_size', self.d))
+
+    @staticmethod
+    def flat_order(model):
+        return ['gru_layers.weight_ih_l0', 'gru_layers.weight_hh_l0', 'gru_layers.bias_ih_l0', 'gru_layers.bias_hh_l0',
+                'dense.weight', 'dense.bias']
+
+    def forward(self, item_seq, save=True, **_):
+        eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
+        B, L = item_seq.shape
+        d, Hd, prec = self.d, self.Hd, eng.prec
+        table = eng.table_for_seq().data
+        x = ws.get('gru_x', (B * L, d))
+        ops.gather_rows(table, item_seq, out=x)
+        gi = ws.get('gru_gi', (B * L, 3 * Hd))
+        _lin_fwd(x, B * L, d, fp.p('gru_layers.weight_ih_l0'), fp.p('gru_layers.bias_ih_l0'), 3 * Hd, gi, prec=prec)
+        hs = ws.get('gru_h', (L + 1, B, Hd))
+        hs[0].zero_()
+        save_g = ws.get('gru_save', (L, B, 4 * Hd))
+        gh = ws.get('gru_gh', (B, 3 * Hd))
+        w_hh, b_hh = fp.p('gru_layers.weight_hh_l0'), fp.p('gru_layers.bias_hh_l0')
+        for t in range(L):
+            _lin_fwd(hs[t], B, Hd, w_hh, b_hh, 3 * Hd, gh, prec=prec)
+            ops.gru_gate_fwd(gi[t:], L * 3 * Hd, gh, hs[t], hs[t + 1], save_g[t], B, Hd)
+        user = ws.get('user_emb', (B, d))
+        _lin_fwd(hs[L], B, Hd, fp.p('dense.weight'), fp.p('dense.bias'), d, user, prec=prec)
+        self.item_seq, self.x, self.hs, self.save_g = item_seq, x, hs, save_g
+        return user
+
+    def backward(self, d_user):
+        eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
+        item_seq = self.item_seq
+        B, L = item_seq.shape
+        d, Hd, prec = self.d, self.Hd, eng.prec
+        hs, save_g = self.hs, self.save_g
+        dh = ws.get('gru_dh_a', (B, Hd))
+        _lin_bwd(d_user, B, d, hs[L], Hd, fp.p('dense.weight'), dh, fp.g('dense.weight'), fp.g('dense.bias'), prec=prec)
+        dgi = ws.get('gru_dgi', (B * L, 3 * Hd))
+        dgh_all = ws.get('gru_dgh', (L, B, 3 * Hd))
+        w_hh = fp.p('gru_layers.weight_hh_l0')
+        for t in reversed(range(L)):
+            dh_prev = ws.get('gru_dh_b' if (L - t) % 2 else 'gru_dh_a', (B, Hd))
+            ops.gru_gate_bwd(dh, save_g[t], hs[t], dgi[t:], L * 3 * Hd, dgh_all[t], dh_prev, B, Hd)
+            ops.gemm(dgh_all[t], w_hh, dh_prev, B, Hd, 3 * Hd, accumulate=True, precision=prec)
+            dh = dh_prev
+        # weight gradients over all steps at once
+        ops.gemm(dgh_all, hs, fp.g('gru_layers.weight_hh_l0'), 3 * Hd, Hd, L * B, transA=True, lda=3 * Hd, ldb=Hd,
+                 accumulate=True, precision=prec)
+        ops.colsum_accum(dgh_all, L * B, 3 * Hd, fp.g('gru_layers.bias_hh_l0'))
+        drows = ws.get('drows', (B * L, d))
+        _lin_bwd(dgi, B * L, 3 * Hd, self.x, d, fp.p('gru_layers.weight_ih_l0'), drows, fp.g('gru_layers.weight_ih_l0'),
+                 fp.g('gru_layers.bias_ih_l0'), prec=prec)
+        eng.rowgrad(eng.table_for_seq()).add(item_seq, drows, 1, None, 1)
+
+
+class PoolTower:
+    """AvgHist (avghist.py:34-42), SVD++ (svdplusplus.py:31-39) and MF (recommender.py:42-44): sum-pool of the history
+    rows (+ user row).  Backward produces no activations at all: the row gradient of history item (b,l) is
+    coeff[b] * d_user[b], expressed as a (source row, coefficient) pair for the row-sparse optimizer."""
+
+    def __init__(self, eng, cfg, use_seq, use_user):
+        self.eng, self.use_seq, self.use_user = eng, use_seq, use_user
+        self.alpha = float(cfg.get('user_sequence_alpha', 0.5))
+        self.d = int(cfg['embedding_size'])
+
+    @staticmethod
+    def flat_order(model):
+        return []
+
+    def forward(self, item_seq=None, item_seq_len=None, user_id=None, save=True, **_):
+        eng, ws = self.eng, self.eng.ws
+        utable = eng.model.user_embedding.weight if self.use_user else None
+        if not self.use_seq:
+            B = user_id.shape[0]
+            user = ws.get('user_emb', (B, self.d))
+            ops.gather_rows(utable.data, user_id, out=user)
+        else:
+            B = item_seq.shape[0]
+            user = ws.get('user_emb', (B, self.d))
+            self.coeff = ws.get('pool_coeff', (B,))
+            ops.pool_sum_fwd(eng.table_for_seq().data, item_seq, item_seq_len, self.alpha,
+                             utable.data if utable is not None else None, user_id, out=user, coeff_out=self.coeff)
+        self.item_seq, self.user_id = item_seq, user_id
+        return user
+
+    def backward(self, d_user):
+        eng = self.eng
+        if self.use_seq:
+            L = self.item_seq.shape[1]
+            eng.rowgrad(eng.table_for_seq()).add(self.item_seq, d_user, L, self.coeff, L)
+        if self.use_user:
+            eng.rowgrad(eng.model.user_embedding.weight).add(self.user_id, d_user, 1, None, 1)
+
+
+# ==================================================================================================
+class Engine:
+    def __init__(self, model, tower_kind: str):
+        self.model = model
+        self.cfg = model.config
+        self.device = None
+        self.flat: Optional[FlatParams] = None
+        self.ws: Optional[Workspace] = None
+        self.tower_kind = tower_kind
+        self.tower = None
+        self.prec = PRECISION_CODES[str(self.cfg.get('gemm_precision', 'fp32'))]
+        self._rowgrads: Dict[int, RowGrad] = {}
+        self.dense_table_grads = False      # exact-dense mode (reference autograd semantics)
+        self.nan_flag = None
+        self.last = None
+
+    # ---- setup ------------------------------------------------------------------------------
+    def table_for_seq(self):
+        m = self.model
+        return m.item_dst_embedding.weight if hasattr(m, 'item_dst_embedding') else m.item_embedding.weight
+
+    def table_for_target(self):
+        return self.model.item_embedding.weight
+
+    def table_params(self):
+        m = self.model
+        out, seen = [], set()
+        for name in ('user_embedding', 'item_embedding', 'item_dst_embedding'):
+            mod = getattr(m, name, None)
+            if mod is not None and id(mod.weight) not in seen:
+                seen.add(id(mod.weight))
+                out.append(mod.weight)
+        return out
+
+    def rowgrad(self, param) -> RowGrad:
+        rg = self._rowgrads.get(id(param))
+        if rg is None:
+            rg = self._rowgrads[id(param)] = RowGrad(param)
+        return rg
+
+    def rowgrads(self):
+        return [self.rowgrad(p) for p in self.table_params()]
+
+    def ensure_ready(self):
+        dev = self.model.item_embedding.weight.device
+        if dev.type != 'cuda':
+            raise RuntimeError('unirec_b200 models run on CUDA (sm_100a) only: the hot path is hand-written CUDA with no '
+                               'CPU fallback. Move the model with .to("cuda") / config device.')
+        if self.device == dev and self.flat is not None:
+            return
+        self.device = dev
+        m, cfg = self.model, self.cfg
+        if self.tower_kind == 'sasrec':
+            self.tower = SASRecTower(self, cfg)
+            order = SASRecTower.flat_order(m)
+        elif self.tower_kind == 'gru':
+            self.tower = GRUTower(self, cfg)
+            order = GRUTower.flat_order(m)
+        else:
+            self.tower = PoolTower(self, cfg, use_seq=self.tower_kind in ('avghist', 'svdpp'),
+                                   use_user=self.tower_kind in ('svdpp', 'mf'))
+            order = []
+        named = dict(m.named_parameters())
+        table_ids = {id(p) for p in self.table_params()}
+        rest = [n for n, p in named.items() if n not in order and id(p) not in table_ids]
+        self.dense_names = order + rest        # user_bias / item_bias (and anything else) follow the tower params
+        self.flat = FlatParams([(n, named[n]) for n in self.dense_names], dev)
+        for p in self.table_params():
+            if not p.data.is_contiguous():
+                p.data = p.data.contiguous()
+        self.ws = Workspace(dev)
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._rowgrads = {}
+
+    # ---- forward / backward ---------------------------------------------------------------------
+    def user_emb(self, save=False, **batch):
+        self.ensure_ready()
+        return self.tower.forward(save=save, **batch)
+
+    def scores_only(self, user_emb, item_id, user_id=None):
+        """_predict_layer without loss (eval / predict): recommender.py:76-96."""
+        m, ws = self.model, self.ws
+        item_id2 = item_id.view(item_id.shape[0], -1).contiguous()
+        B, N = item_id2.shape
+        scores = torch.empty(B, N, dtype=torch.float32, device=self.device)
+        lv = ws.get('loss_vec_eval', (B,))
+        # forward-only: softmax branch handles N == 1
+        ops.score_loss(self.table_for_target().data, user_emb, item_id2, 'softmax',
+                       item_bias=m.item_bias.data if m.has_item_bias else None,
+                       user_bias=m.user_bias.data if m.has_user_bias else None, user_id=user_id, tau=m.tau,
+                       score_clip=m.SCORE_CLIP, norm_host=1.0, scores=scores, loss_vec=lv)
+        return scores.view(item_id.shape)
+
+    def forward_loss(self, user_id=None, item_id=None, label=None, item_seq=None, item_seq_len=None, reduction=True,
+                     want_scores=False):
+        self.ensure_ready()
+        m, ws = self.model, self.ws
+        if m.group_size > 0:
+            item_id = item_id.view(-1, m.group_size)
+            label = label.view(-1, m.group_size) if label is not None else None
+        if item_id.dim() == 1:
+            item_id = item_id.view(-1, 1)
+            label = label.view(-1, 1) if label is not None else None
+        item_id = item_id.contiguous()
+        B, N = item_id.shape
+        for rg in self._rowgrads.values():
+            rg.reset()
+        user = self.tower.forward(item_seq=item_seq, item_seq_len=item_seq_len, user_id=user_id, save=True)
+        loss_type = m.loss_type
+        scores = ws.get('scores', (B, N))
+        loss_vec = ws.get('loss_vec', (B,))
+        dscore = ws.get('dscore', (B, N))
+        grad_user = ws.get('grad_user', (B, user.shape[1]))
+        norm_dev, norm_host = None, float(B * max(N - 1, 1))
+        if loss_type == 'softmax':
+            if label is not None:
+                label = label.contiguous()
+                norm_dev = ws.get('n_pos', (1,))
+                ops.count_positive(label, norm_dev)
+            else:
+                norm_host = float(B)
+        ops.score_loss(self.table_for_target().data, user, item_id, loss_type, label=label if loss_type == 'softmax' else None,
+                       item_bias=m.item_bias.data if m.has_item_bias else None,
+                       user_bias=m.user_bias.data if m.has_user_bias else None, user_id=user_id, tau=m.tau,
+                       score_clip=m.SCORE_CLIP, norm_dev=norm_dev, norm_host=norm_host, scores=scores, loss_vec=loss_vec,
+                       dscore=dscore, grad_user=grad_user)
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        if loss_type == 'softmax':
+            ops.loss_finish(loss_vec, loss, denom_dev=norm_dev, denom_host=norm_host, nan_flag=self.nan_flag)
+        else:
+            ops.loss_finish(loss_vec, loss, denom_host=float(B), nan_flag=self.nan_flag)
+        self.last = dict(user=user, item_id=item_id, user_id=user_id, dscore=dscore, grad_user=grad_user, B=B, N=N)
+        out_loss = loss if reduction else loss_vec.clone()
+        return out_loss, (scores if want_scores else None), user
+
+    def backward(self, grad_out=None):
+        """Backward of the last forward_loss.  Dense grads are ACCUMULATED into flat.grad; table grads are
+        registered as row lists.  `grad_out` (dLoss upstream) is applied only when given."""
+        st, m = self.last, self.model
+        d_user, dscore = st['grad_user'], st['dscore']
+        if grad_out is not None:
+            d_user = d_user * grad_out
+            dscore = dscore * grad_out
+        fp = self.flat
+        if m.has_item_bias:
+            gb = fp.g('item_bias')
+            gb.index_add_(0, st['item_id'].reshape(-1), dscore.reshape(-1))
+        if m.has_user_bias:
+            fp.g('user_bias').index_add_(0, st['user_id'], dscore.sum(1))
+        self.rowgrad(self.table_for_target()).add(st['item_id'], st['user'], st['N'], dscore, 1)
+        self.tower.backward(d_user)
+
+    def zero_dense_grads(self):
+        if self.flat is not None:
+            self.flat.grad.zero_()

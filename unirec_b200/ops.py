@@ -1,0 +1,223 @@
+"""Thin torch-tensor wrappers over the C ABI (include/unirec_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every function below passes raw device
+pointers to the hand-written sm_100a kernels, launched on torch's current CUDA stream.  There is no CPU or
+eager fallback: a non-CUDA tensor raises.
+"""
+import torch
+
+from . import _cabi
+
+ACT_CODES = {None: 0, 'none': 0, 'swish': 1, 'gelu': 2, 'relu': 3, 'tanh': 4, 'sigmoid': 5}
+LOSS_CODES = {'softmax': 0, 'bpr': 1}
+OPT_CODES = {'adam': 0, 'adamw': 1, 'sgd': 2, 'sqnorm': 3}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('unirec_b200 ops need CUDA tensors (no CPU fallback exists); got device %s' % t.device)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError('expected %s, got %s' % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def _f32(t):
+    return _ptr(t, torch.float32)
+
+
+def _idx_bits(idx):
+    if idx.dtype == torch.int32:
+        return 32
+    if idx.dtype == torch.int64:
+        return 64
+    raise TypeError('index tensor must be int32 or int64, got %s' % idx.dtype)
+
+
+def _call(name, *args):
+    _cabi.check(getattr(_cabi.lib(), name)(*args), name)
+
+
+def version():
+    return _cabi.lib().ur_version()
+
+
+def has_tensor_core_gemm():
+    return bool(_cabi.lib().ur_has_tensor_core_gemm())
+
+
+# ------------------------------------------------------------------ rows
+def gather_rows(table, idx, out=None):
+    assert table.dim() == 2 and table.is_contiguous() and idx.is_contiguous()
+    d = table.shape[1]
+    if out is None:
+        out = torch.empty(*idx.shape, d, dtype=torch.float32, device=table.device)
+    _call('ur_gather_rows_f32', _f32(table), table.shape[0], d, _ptr(idx), _idx_bits(idx), idx.numel(), _f32(out), _stream())
+    return out
+
+
+def scatter_add_rows(grad, idx, src, src_group=1, coef=None, coef_group=1, pad_id=0):
+    assert grad.is_contiguous() and idx.is_contiguous() and src.is_contiguous()
+    _call('ur_scatter_add_rows_f32', _f32(grad), grad.shape[0], grad.shape[1], _ptr(idx), _idx_bits(idx), idx.numel(),
+          _f32(src), src_group, _f32(coef), coef_group, pad_id, _stream())
+    return grad
+
+
+def pool_sum_fwd(table, item_seq, item_seq_len, alpha, user_table=None, user_id=None, out=None, coeff_out=None):
+    B, L = item_seq.shape
+    d = table.shape[1]
+    if out is None:
+        out = torch.empty(B, d, dtype=torch.float32, device=table.device)
+    _call('ur_pool_sum_fwd_f32', _f32(table), d, _ptr(item_seq, torch.int32), B, L, _ptr(item_seq_len, torch.int64),
+          float(alpha), _f32(user_table), _ptr(user_id, torch.int64) if user_id is not None else None, _f32(out),
+          _f32(coeff_out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ layer norm family
+def seq_prep_ln_fwd(table, pos, gamma, beta, eps, item_seq, Y, mean, rstd):
+    B, L = item_seq.shape
+    _call('ur_seq_prep_ln_fwd_f32', _f32(table), _f32(pos), _f32(gamma), _f32(beta), float(eps),
+          _ptr(item_seq, torch.int32), B, L, table.shape[1], _f32(Y), _f32(mean), _f32(rstd), _stream())
+    return Y
+
+
+def seq_prep_ln_bwd(table, pos, gamma, item_seq, mean, rstd, dY, dX, dgamma, dbeta, dpos):
+    B, L = item_seq.shape
+    _call('ur_seq_prep_ln_bwd_f32', _f32(table), _f32(pos), _f32(gamma), _ptr(item_seq, torch.int32), B, L,
+          table.shape[1], _f32(mean), _f32(rstd), _f32(dY), _f32(dX), _f32(dgamma), _f32(dbeta), _f32(dpos), _stream())
+    return dX
+
+
+def add_ln_fwd(X, R, gamma, beta, eps, Y, mean, rstd, rows=None, d=None, ldx=None, ldr=None, ldy=None):
+    d = d or X.shape[-1]
+    rows = rows if rows is not None else X.numel() // d
+    _call('ur_add_ln_fwd_f32', _f32(X), ldx or d, _f32(R), ldr or d, _f32(gamma), _f32(beta), float(eps), rows, d,
+          _f32(Y), ldy or d, _f32(mean), _f32(rstd), _stream())
+    return Y
+
+
+def add_ln_bwd(Z, gamma, mean, rstd, dY, dZ, dgamma, dbeta, dExtra=None, rows=None, d=None, ldz=None, lddy=None,
+               ldde=None, lddz=None):
+    d = d or Z.shape[-1]
+    rows = rows if rows is not None else Z.numel() // d
+    _call('ur_add_ln_bwd_f32', _f32(Z), ldz or d, _f32(gamma), _f32(mean), _f32(rstd), _f32(dY), lddy or d,
+          _f32(dExtra), ldde or d, rows, d, _f32(dZ), lddz or d, _f32(dgamma), _f32(dbeta), _stream())
+    return dZ
+
+
+# ------------------------------------------------------------------ GEMM
+def gemm(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, act=None,
+         preact=None, ldp=None, accumulate=False, precision=0):
+    """C[M,N] (+)= act(op(A)[M,K] @ op(B)[K,N] + bias).  Row-major; default leading dims = stored row length."""
+    if lda is None:
+        lda = M if transA else K
+    if ldb is None:
+        ldb = K if transB else N
+    if ldc is None:
+        ldc = N
+    _call('ur_gemm_f32', int(transA), int(transB), M, N, K, _f32(A), lda, _f32(B), ldb, _f32(C), ldc, _f32(bias),
+          ACT_CODES[act], _f32(preact), ldp or N, int(accumulate), int(precision), _stream())
+    return C
+
+
+def act_bwd(dY, preact, act):
+    _call('ur_act_bwd_f32', _f32(dY), _f32(preact), dY.numel(), ACT_CODES[act], _stream())
+    return dY
+
+
+def colsum_accum(X, M, N, out, ldx=None):
+    _call('ur_colsum_accum_f32', _f32(X), ldx or N, M, N, _f32(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ attention
+def attn_fwd(qkv, item_seq, H, dh, causal, ctx, lse, q_only_last=False):
+    B, L = item_seq.shape
+    _call('ur_attn_fwd_f32', _f32(qkv), _ptr(item_seq, torch.int32), B, L, H, dh, int(causal), int(q_only_last),
+          _f32(ctx), _f32(lse), _stream())
+    return ctx
+
+
+def attn_bwd(qkv, item_seq, H, dh, causal, ctx, lse, dctx, dqkv, q_only_last=False):
+    B, L = item_seq.shape
+    _call('ur_attn_bwd_f32', _f32(qkv), _ptr(item_seq, torch.int32), B, L, H, dh, int(causal), int(q_only_last),
+          _f32(ctx), _f32(lse), _f32(dctx), _f32(dqkv), _stream())
+    return dqkv
+
+
+# ------------------------------------------------------------------ GRU pointwise
+def gru_gate_fwd(gi, ld_gi, gh, h_prev, h_out, save, B, H):
+    _call('ur_gru_gate_fwd_f32', _f32(gi), ld_gi, _f32(gh), _f32(h_prev), _f32(h_out), _f32(save), B, H, _stream())
+
+
+def gru_gate_bwd(dh, save, h_prev, dgi, ld_dgi, dgh, dh_prev, B, H):
+    _call('ur_gru_gate_bwd_f32', _f32(dh), _f32(save), _f32(h_prev), _f32(dgi), ld_dgi, _f32(dgh), _f32(dh_prev), B, H,
+          _stream())
+
+
+# ------------------------------------------------------------------ fused score + loss
+def score_loss(table, user_emb, item_id, loss_type, label=None, item_bias=None, user_bias=None, user_id=None, tau=1.0,
+               score_clip=-1.0, norm_dev=None, norm_host=1.0, scores=None, loss_vec=None, dscore=None, grad_user=None):
+    B, N = item_id.shape
+    _call('ur_score_loss_fwd_bwd_f32', _f32(table), table.shape[1], _f32(user_emb), _ptr(item_id, torch.int64), B, N,
+          _ptr(label, torch.int32) if label is not None else None, _f32(item_bias), _f32(user_bias),
+          _ptr(user_id, torch.int64) if user_id is not None else None, float(tau), float(score_clip),
+          LOSS_CODES[loss_type], _f32(norm_dev), float(norm_host), _f32(scores), _f32(loss_vec), _f32(dscore),
+          _f32(grad_user), _stream())
+
+
+def count_positive(label, out):
+    _call('ur_count_positive_i32', _ptr(label, torch.int32), label.numel(), _f32(out), _stream())
+    return out
+
+
+def loss_finish(loss_vec, loss_out, denom_dev=None, denom_host=1.0, nan_flag=None):
+    _call('ur_loss_finish_f32', _f32(loss_vec), loss_vec.numel(), _f32(denom_dev), float(denom_host), _f32(loss_out),
+          _ptr(nan_flag, torch.int32) if nan_flag is not None else None, _stream())
+    return loss_out
+
+
+# ------------------------------------------------------------------ row-sparse optimizer
+def rowlist_link(head, keys, entry_offset, nxt, uniq, n_uniq, pad_id=0):
+    _call('ur_rowlist_link', _ptr(head, torch.int32), _ptr(keys), _idx_bits(keys), keys.numel(), entry_offset,
+          _ptr(nxt, torch.int32), _ptr(uniq, torch.int32), _ptr(n_uniq, torch.int32), pad_id, _stream())
+
+
+def rowlist_apply(table, mom, var, head, nxt, uniq, n_uniq, max_uniq, sources, mode, lr=0.0, beta1=0.9, beta2=0.999,
+                  eps=1e-8, weight_decay=0.0, step_dev=None, grad_scale_dev=None, skip_flag=None, sqnorm_out=None):
+    """sources: list of 1 or 2 tuples (src, src_group, coef_or_None, coef_group, n_entries)."""
+    s0 = sources[0]
+    s1 = sources[1] if len(sources) > 1 else (None, 1, None, 1, 0)
+    _call('ur_rowlist_apply_f32', _f32(table), _f32(mom), _f32(var), table.shape[1], _ptr(head, torch.int32),
+          _ptr(nxt, torch.int32), _ptr(uniq, torch.int32), _ptr(n_uniq, torch.int32), max_uniq,
+          _f32(s0[0]), s0[1], _f32(s0[2]), s0[3], s0[4], _f32(s1[0]), s1[1], _f32(s1[2]), s1[3],
+          OPT_CODES[mode], float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+          _ptr(step_dev, torch.int32) if step_dev is not None else None, _f32(grad_scale_dev),
+          _ptr(skip_flag, torch.int32) if skip_flag is not None else None, _f32(sqnorm_out), _stream())
+
+
+def dense_opt(param, grad, mom, var, mode, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step_dev=None,
+              grad_scale_dev=None, skip_flag=None):
+    _call('ur_dense_opt_f32', _f32(param), _f32(grad), _f32(mom), _f32(var), param.numel(), OPT_CODES[mode], float(lr),
+          float(beta1), float(beta2), float(eps), float(weight_decay),
+          _ptr(step_dev, torch.int32) if step_dev is not None else None, _f32(grad_scale_dev),
+          _ptr(skip_flag, torch.int32) if skip_flag is not None else None, _stream())
+
+
+def sqnorm_accum(grad, sqnorm):
+    _call('ur_sqnorm_accum_f32', _f32(grad), grad.numel(), _f32(sqnorm), _stream())
+
+
+def clip_coef(sqnorm, max_norm, coef):
+    _call('ur_clip_coef_f32', _f32(sqnorm), float(max_norm), _f32(coef), _stream())
+
+
+def step_advance(step, skip_flag=None):
+    _call('ur_step_advance', _ptr(step, torch.int32), _ptr(skip_flag, torch.int32) if skip_flag is not None else None,
+          _stream())
