@@ -125,6 +125,24 @@ int ur_sqnorm_accum_f32(const float* grad, int64_t n, float* sqnorm, void* strea
 int ur_clip_coef_f32(const float* sqnorm, float max_norm, float* coef, void* stream);
 int ur_step_advance(int32_t* step, const int32_t* skip_flag, void* stream);
 
+/* ---- Row-sharded tables (multi-GPU): rank r of `world` owns rows {id : id % world == r} at local index id / world.
+ * These replace the reference's replicated tables + DDP all-reduce of dense [V,d] gradients
+ * (unirec/model/base/reco_abc.py:167-170, unirec/facility/trainer.py:67,346) together with NCCL collectives issued by the host
+ * (all-gather of ids / user vectors, reduce-scatter of per-sample partial states): see unirec_b200/sharding.py. */
+int ur_shard_gather_rows_f32(const float* table_local, int d, const void* idx, int idx_bits, int64_t n, int world, int rank,
+                             float* out, void* stream);
+int ur_shard_localize(const void* idx, int idx_bits, int64_t n, int world, int rank, int64_t pad_id, int32_t* out, void* stream);
+/* one pass over the OWNED target rows of all S samples: state[s] = (max, sum exp, sum y*s, sum y, sum p*e [d], sum y*e [d]) */
+int ur_score_partial_f32(const float* table_local, int d, const float* user_emb, const int64_t* item_id, int64_t S, int N,
+                         const int32_t* label /*nullable*/, const float* item_bias /*nullable*/, const float* user_bias /*nullable*/,
+                         const int64_t* user_id, float tau, float score_clip, int world, int rank, float* z, float* state,
+                         void* stream);
+int ur_score_rescale_f32(float* state, const float* gmax, int64_t S, int d, void* stream);
+int ur_score_finish_f32(const float* state, const float* gmax, int64_t B, int d, float tau, const float* norm_dev, float* loss_vec,
+                        float* lse_ny, float* grad_user, void* stream);
+int ur_score_dscore_f32(const float* z, const int64_t* item_id, const int32_t* label /*nullable*/, const float* lse_ny, int64_t S,
+                        int N, int world, int rank, float tau, float score_clip, const float* norm_dev, float* dscore, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

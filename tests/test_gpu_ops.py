@@ -184,10 +184,10 @@ def test_attention_fwd_bwd(L, H, dh, causal):
     lse = torch.empty(B, H, L, device=DEV)
     qd, sd = qkv.to(DEV).view(B * L, 3 * d), seq.to(DEV)
     ops.attn_fwd(qd, sd, H, dh, causal, ctx, lse)
-    assert rel(ctx.view(B, L, d), ctx_ref) < 1e-4
+    assert rel(ctx.view(B, L, d), ctx_ref) < 5e-4
     dqkv = torch.zeros(B * L, 3 * d, device=DEV)
     ops.attn_bwd(qd, sd, H, dh, causal, ctx, lse, dctx.to(DEV).view(B * L, d), dqkv)
-    assert rel(dqkv.view(B, L, 3 * d), qr.grad) < 1e-4
+    assert rel(dqkv.view(B, L, 3 * d), qr.grad) < 5e-4     # __expf-based softmax; bar is 1e-3
 
 
 @pytest.mark.parametrize('loss_type', ['softmax', 'bpr'])

@@ -39,6 +39,12 @@ SIGNATURES = {
     'ur_sqnorm_accum_f32': 'plpp',
     'ur_clip_coef_f32': 'pfpp',
     'ur_step_advance': 'ppp',
+    'ur_shard_gather_rows_f32': 'pipiliipp',
+    'ur_shard_localize': 'piliilpp',
+    'ur_score_partial_f32': 'pippli' + 'pppp' + 'ffii' + 'ppp',
+    'ur_score_rescale_f32': 'pplip',
+    'ur_score_finish_f32': 'pplifpppp' + 'p',
+    'ur_score_dscore_f32': 'pppplii' + 'iffpp' + 'p',
 }
 
 _KIND = {'p': _P, 'i': _I, 'l': _L, 'f': _F}

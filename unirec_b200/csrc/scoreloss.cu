@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) score_loss_kernel(const ScoreLossParams p
 
     // shared layout
     float* zbuf = smem;                                  // [spb][N]      scaled, unclamped scores
-    float* gstate = zbuf + (size_t)spb * N;              // [spb][G][4]
+    float* gstate = zbuf + (((size_t)spb * N + 3) & ~(size_t)3);   // [spb][G][4]  (16-byte aligned: gacc/aux take float4)
     float* gacc = gstate + spb * G * 4;                  // [spb][G][D]
     float* aux = gacc + (size_t)spb * G * D;             // [spb][D]      softmax: sum_j y_j m_j e_j ; bpr: e_0
 
@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(256) score_loss_kernel(const ScoreLossParams p
 
     if (live) {
         const int jstart = LOSS == 1 ? 1 : 0;
-        for (int j0 = jstart + g; j0 < N; j0 += G * U) {
+        // trip count is uniform across the warp (row groups differ only in the offset g): shuffles stay convergent
+        for (int jb = jstart; jb < N; jb += G * U) {
+            const int j0 = jb + g;
             float4 row[U][VPL];
             float bias[U];
             int32_t y[U];
@@ -124,11 +126,14 @@ __global__ void __launch_bounds__(256) score_loss_kernel(const ScoreLossParams p
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int j = j0 + u * G;
+                // the shuffle reduction is executed by ALL lanes (row groups of one warp may disagree on j < N)
+                float dot = 0.f;
                 if (j < N) {
-                    float dot = 0.f;
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) dot += f4_dot(row[u][v], uvec[v]);
-                    dot = group_sum<LPR>(dot);
+                }
+                dot = group_sum<LPR>(dot);
+                if (j < N) {
                     const float z = (dot + ub + bias[u]) * p.inv_tau;
                     const float s = has_clip ? fminf(fmaxf(z, -clip), clip) : z;
                     const float mask = (has_clip && (z < -clip || z > clip)) ? 0.f : 1.f;
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(256) count_positive_kernel(const int32_t* __re
 static size_t score_loss_smem(int d, int N, int wps) {
     const int d4 = d / 4, lpr = d4 < 32 ? d4 : 32, rpw = 32 / lpr;
     const int spb = 8 / wps, G = wps * rpw;
-    return sizeof(float) * ((size_t)spb * N + (size_t)spb * G * 4 + (size_t)spb * G * d + (size_t)spb * d);
+    return sizeof(float) * ((((size_t)spb * N + 3) & ~(size_t)3) + (size_t)spb * G * 4 + (size_t)spb * G * d + (size_t)spb * d);
 }
 
 template <int D4>

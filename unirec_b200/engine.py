@@ -85,6 +85,7 @@ class RowGrad:
         self.n_uniq = None
         self.specs = []            # list of (keys, src, src_group, coef, coef_group)
         self.linked = False
+        self.pad_id = 0            # key value that is skipped (global padding id; -1 for localized shard keys)
 
     def reset(self):
         self.specs = []
@@ -115,7 +116,7 @@ class RowGrad:
         self.n_uniq.zero_()
         off = 0
         for keys, *_ in self.specs:
-            ops.rowlist_link(self.head, keys, off, self.next, self.uniq, self.n_uniq, pad_id=0)
+            ops.rowlist_link(self.head, keys, off, self.next, self.uniq, self.n_uniq, pad_id=self.pad_id)
             off += keys.numel()
         self.linked = True
 
@@ -126,7 +127,7 @@ class RowGrad:
         """Exact-dense mode: materialise the [V,d] gradient the reference's autograd would produce."""
         g = torch.zeros_like(self.param.data)
         for keys, src, sg, coef, cg in self.specs:
-            ops.scatter_add_rows(g, keys, src, sg, coef, cg, pad_id=0)
+            ops.scatter_add_rows(g, keys, src, sg, coef, cg, pad_id=self.pad_id)
         return g
 
 
@@ -181,11 +182,12 @@ class SASRecTower:
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
         B, L = item_seq.shape
         d, I, H, T, prec = self.d, self.I, self.H, B * L, eng.prec
-        table = eng.table_for_seq().data
+        table, index = eng.seq_rows_source(item_seq)
+        self.seq_src = (table, index)
         pos = fp.p('position_embedding.weight') if self.causal else None
         x = ws.get('x0', (T, d))
         self.mean0, self.rstd0 = ws.get('mean0', (T,)), ws.get('rstd0', (T,))
-        ops.seq_prep_ln_fwd(table, pos, fp.p('LayerNorm.weight'), fp.p('LayerNorm.bias'), self.eps, item_seq, x,
+        ops.seq_prep_ln_fwd(table, pos, fp.p('LayerNorm.weight'), fp.p('LayerNorm.bias'), self.eps, index, x,
                             self.mean0, self.rstd0)
         self.saved = []
         for i in range(self.n_layers):
@@ -253,13 +255,13 @@ class SASRecTower:
             # dx = dz1 (residual) + dqkv @ Wqkv  -> accumulate into dz1
             _lin_bwd(dqkv, T, 3 * d, x, d, wqkv, dz1, gwqkv, gbqkv, accumulate_dx=True, prec=prec)
             dx = dz1
-        table = eng.table_for_seq()
+        table, index = self.seq_src
         pos = fp.p('position_embedding.weight') if self.causal else None
         drows = ws.get('drows', (T, d))
-        ops.seq_prep_ln_bwd(table.data, pos, fp.p('LayerNorm.weight'), item_seq, self.mean0, self.rstd0, dx, drows,
+        ops.seq_prep_ln_bwd(table, pos, fp.p('LayerNorm.weight'), index, self.mean0, self.rstd0, dx, drows,
                             fp.g('LayerNorm.weight'), fp.g('LayerNorm.bias'),
                             fp.g('position_embedding.weight') if self.causal else None)
-        eng.rowgrad(table).add(item_seq, drows, 1, None, 1)
+        eng.add_seq_rowgrad(item_seq, drows)
 
 
 class GRUTower:
@@ -280,9 +282,9 @@ class GRUTower:
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
         B, L = item_seq.shape
         d, Hd, prec = self.d, self.Hd, eng.prec
-        table = eng.table_for_seq().data
+        table, index = eng.seq_rows_source(item_seq)
         x = ws.get('gru_x', (B * L, d))
-        ops.gather_rows(table, item_seq, out=x)
+        ops.gather_rows(table, index, out=x)
         gi = ws.get('gru_gi', (B * L, 3 * Hd))
         _lin_fwd(x, B * L, d, fp.p('gru_layers.weight_ih_l0'), fp.p('gru_layers.bias_ih_l0'), 3 * Hd, gi, prec=prec)
         hs = ws.get('gru_h', (L + 1, B, Hd))
@@ -321,7 +323,7 @@ class GRUTower:
         drows = ws.get('drows', (B * L, d))
         _lin_bwd(dgi, B * L, 3 * Hd, self.x, d, fp.p('gru_layers.weight_ih_l0'), drows, fp.g('gru_layers.weight_ih_l0'),
                  fp.g('gru_layers.bias_ih_l0'), prec=prec)
-        eng.rowgrad(eng.table_for_seq()).add(item_seq, drows, 1, None, 1)
+        eng.add_seq_rowgrad(item_seq, drows)
 
 
 class PoolTower:
@@ -436,6 +438,14 @@ class Engine:
         self.ws = Workspace(dev)
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._rowgrads = {}
+
+    # ---- sequence-row hooks (overridden by the row-sharded engine) -------------------------------
+    def seq_rows_source(self, item_seq):
+        """(table, index) such that table[index] are the history rows of the local batch."""
+        return self.table_for_seq().data, item_seq
+
+    def add_seq_rowgrad(self, item_seq, drows):
+        self.rowgrad(self.table_for_seq()).add(item_seq, drows, 1, None, 1)
 
     # ---- forward / backward ---------------------------------------------------------------------
     def user_emb(self, save=False, **batch):

@@ -39,8 +39,30 @@ def _idx_bits(idx):
     raise TypeError('index tensor must be int32 or int64, got %s' % idx.dtype)
 
 
+# measurement hooks (bench.py): number of C-ABI kernel launches; CUDA-event pairs around one named entry point
+# (TIMED_OP) or around every entry point (PROFILE dict).  All off by default.
+LAUNCH_COUNT = 0
+TIMED_OP = None
+TIMED_EVENTS = []
+PROFILE = None
+
+
 def _call(name, *args):
-    _cabi.check(getattr(_cabi.lib(), name)(*args), name)
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
+    fn = getattr(_cabi.lib(), name)
+    if PROFILE is not None or name == TIMED_OP:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        if name == TIMED_OP:
+            TIMED_EVENTS.append((a, b))
+        if PROFILE is not None:
+            PROFILE.setdefault(name, []).append((a, b))
+    else:
+        rc = fn(*args)
+    _cabi.check(rc, name)
 
 
 def version():
@@ -221,3 +243,39 @@ def clip_coef(sqnorm, max_norm, coef):
 def step_advance(step, skip_flag=None):
     _call('ur_step_advance', _ptr(step, torch.int32), _ptr(skip_flag, torch.int32) if skip_flag is not None else None,
           _stream())
+
+
+# ------------------------------------------------------------------ row-sharded tables (multi-GPU)
+def shard_gather_rows(table_local, idx, world, rank, out):
+    _call('ur_shard_gather_rows_f32', _f32(table_local), table_local.shape[1], _ptr(idx), _idx_bits(idx), idx.numel(), world,
+          rank, _f32(out), _stream())
+    return out
+
+
+def shard_localize(idx, world, rank, out, pad_id=0):
+    _call('ur_shard_localize', _ptr(idx), _idx_bits(idx), idx.numel(), world, rank, pad_id, _ptr(out, torch.int32), _stream())
+    return out
+
+
+def score_partial(table_local, user_emb, item_id, world, rank, z, state, label=None, item_bias=None, user_bias=None,
+                  user_id=None, tau=1.0, score_clip=-1.0):
+    S, N = item_id.shape
+    _call('ur_score_partial_f32', _f32(table_local), table_local.shape[1], _f32(user_emb), _ptr(item_id, torch.int64), S, N,
+          _ptr(label, torch.int32) if label is not None else None, _f32(item_bias), _f32(user_bias),
+          _ptr(user_id, torch.int64) if user_id is not None else None, float(tau), float(score_clip), world, rank,
+          _f32(z), _f32(state), _stream())
+
+
+def score_rescale(state, gmax, d):
+    _call('ur_score_rescale_f32', _f32(state), _f32(gmax), gmax.numel(), d, _stream())
+
+
+def score_finish(state, gmax, d, tau, norm_dev, loss_vec, lse_ny, grad_user):
+    _call('ur_score_finish_f32', _f32(state), _f32(gmax), gmax.numel(), d, float(tau), _f32(norm_dev), _f32(loss_vec),
+          _f32(lse_ny), _f32(grad_user), _stream())
+
+
+def score_dscore(z, item_id, label, lse_ny, world, rank, tau, score_clip, norm_dev, dscore):
+    S, N = item_id.shape
+    _call('ur_score_dscore_f32', _f32(z), _ptr(item_id, torch.int64), _ptr(label, torch.int32) if label is not None else None,
+          _f32(lse_ny), S, N, world, rank, float(tau), float(score_clip), _f32(norm_dev), _f32(dscore), _stream())

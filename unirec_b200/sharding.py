@@ -1,0 +1,180 @@
+"""Row-sharded embedding tables across the GPUs of one box (replaces the reference's replicated tables +
+DDP all-reduce of dense [V,d] gradients, unirec/facility/trainer.py:67,346).
+
+Layout: rank r of W owns table rows {id : id % W == r}, stored at local index id // W (uniform NVSwitch fabric -> no
+topology awareness needed; modulo spreads popular low ids).  The batch stays data-parallel (B samples per rank).
+
+Per step (all collectives are fixed-size NCCL calls on torch's current stream, no host synchronisation):
+  ids      all_gather(item_id, label, item_seq, user_id)                      -> every rank sees all W*B samples' ids
+  history  owner gathers its rows into a zero-filled [W*B*L, d] buffer        -> reduce_scatter = local batch's rows
+  tower    local (replicated encoder) -> u [B,d];  all_gather(u)              -> U_all [W*B, d]
+  scoring  "move queries, not rows": ur_score_partial over OWNED target rows  -> per-sample online-softmax partials
+           all_reduce(MAX) of the partial maxima, ur_score_rescale, reduce_scatter(SUM) of the partial states
+           ur_score_finish at the home rank -> loss, lse, dLoss/du;  all_gather(lse)
+           ur_score_dscore at the owner     -> per-entry dLoss/d(dot) for owned entries
+  backward tower backward -> dX [B*L,d]; all_gather(dX); owners register (local row, source row, coef) lists
+  update   row-sparse optimizer on the local shard (no exchange); encoder gradients: one all_reduce(SUM) of the flat
+           buffer (the loss is normalised by the GLOBAL positive count, so gradients add across ranks).
+Per-rank HBM traffic equals the single-GPU step (each rank reads 1/W of W batches' rows); NVLink carries ids, [W*B, O(d)]
+states and the history rows.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine import Engine
+
+
+def owner_of(ids, world):
+    return ids % world
+
+
+def local_row(ids, world):
+    return ids // world
+
+
+def local_rows_count(n_rows, world, rank):
+    """Rows of a [n_rows, d] table stored on `rank` (ids rank, rank+W, ...)."""
+    return (n_rows - rank + world - 1) // world
+
+
+def shard_table(full, world, rank):
+    """Local shard of a full table (used by tests and checkpoint import)."""
+    return full[rank::world].contiguous()
+
+
+def unshard_tables(shards):
+    """Inverse of shard_table over the list of per-rank shards."""
+    world = len(shards)
+    n = sum(s.shape[0] for s in shards)
+    out = shards[0].new_empty((n,) + tuple(shards[0].shape[1:]))
+    for r, s in enumerate(shards):
+        out[r::world] = s
+    return out
+
+
+class ShardedEngine(Engine):
+    """Engine whose embedding tables are row-sharded over `dist` ranks.  Softmax loss with SASRec / GRU towers (the
+    north-star multi-GPU configuration); other combinations raise."""
+
+    def __init__(self, model, tower_kind, world, rank, group=None):
+        super().__init__(model, tower_kind)
+        self.world, self.rank, self.group = int(world), int(rank), group
+        if tower_kind not in ('sasrec', 'gru'):
+            raise ValueError('row-sharded tables are implemented for the SASRec and GRU towers')
+        if model.loss_type != 'softmax':
+            raise ValueError('row-sharded tables are implemented for loss_type=softmax')
+
+    def rowgrad(self, param):
+        rg = super().rowgrad(param)
+        rg.pad_id = -1             # keys are localized: -1 = not owned / global padding id
+        return rg
+
+    # ---- collectives --------------------------------------------------------------------------
+    def _all_gather(self, name, t):
+        out = self.ws.get('ag_' + name, (self.world,) + tuple(t.shape), dtype=t.dtype)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def _reduce_scatter(self, name, t):
+        """t: [W, ...] -> sum over ranks of slice [rank]."""
+        out = self.ws.get('rs_' + name, tuple(t.shape[1:]), dtype=t.dtype)
+        dist.reduce_scatter_tensor(out, t, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    # ---- sequence rows ----------------------------------------------------------------------------
+    def seq_rows_source(self, item_seq):
+        B, L = item_seq.shape
+        d = self.table_for_seq().shape[1]
+        seq_all = self._all_gather('seq', item_seq)                       # [W, B, L]
+        self.seq_all = seq_all
+        rows = self.ws.get('seq_rows_all', (self.world, B * L, d))
+        ops.shard_gather_rows(self.table_for_seq().data, seq_all, self.world, self.rank, rows)
+        mine = self._reduce_scatter('seq_rows', rows)                     # [B*L, d] rows of the local batch
+        index = self.ws.get('seq_arange', (B, L), dtype=torch.int32)
+        if getattr(self, '_arange_n', None) != B * L:
+            index.copy_(torch.arange(B * L, dtype=torch.int32, device=self.device).view(B, L))
+            self._arange_n = B * L
+        return mine, index
+
+    def add_seq_rowgrad(self, item_seq, drows):
+        d_all = self._all_gather('drows', drows)                           # [W, B*L, d]
+        keys = self.ws.get('seq_keys_local', (self.seq_all.numel(),), dtype=torch.int32)
+        ops.shard_localize(self.seq_all, self.world, self.rank, keys, pad_id=0)
+        self.rowgrad(self.table_for_seq()).add(keys, d_all.view(-1, d_all.shape[-1]), 1, None, 1)
+
+    # ---- forward / backward ---------------------------------------------------------------------
+    def forward_loss(self, user_id=None, item_id=None, label=None, item_seq=None, item_seq_len=None, reduction=True,
+                     want_scores=False):
+        self.ensure_ready()
+        m, ws, W, r = self.model, self.ws, self.world, self.rank
+        if item_id.dim() == 1:
+            item_id = item_id.view(-1, 1)
+            label = label.view(-1, 1) if label is not None else None
+        item_id = item_id.contiguous()
+        B, N = item_id.shape
+        for rg in self._rowgrads.values():
+            rg.reset()
+        user = self.tower.forward(item_seq=item_seq, item_seq_len=item_seq_len, user_id=user_id, save=True)
+        d = user.shape[1]
+        S = W * B
+        ids_all = self._all_gather('ids', item_id).view(S, N)
+        if label is None:
+            label = ws.get('default_label', (B, N), dtype=torch.int32, zero=True)
+            label[:, 0] = 1
+        lab_all = self._all_gather('label', label.contiguous()).view(S, N)
+        uid_all = self._all_gather('uid', user_id).view(S) if (m.has_user_bias and user_id is not None) else None
+        u_all = self._all_gather('user', user).view(S, d)
+        n_pos = ws.get('n_pos', (1,))
+        ops.count_positive(lab_all, n_pos)                                  # global positives: same value on every rank
+        z = ws.get('z_all', (S, N))
+        state = ws.get('score_state', (S, 4 + 2 * d))
+        ops.score_partial(self.table_for_target().data, u_all, ids_all, W, r, z, state, label=lab_all,
+                          item_bias=m.item_bias.data if m.has_item_bias else None,
+                          user_bias=m.user_bias.data if m.has_user_bias else None, user_id=uid_all, tau=m.tau,
+                          score_clip=m.SCORE_CLIP)
+        gmax = ws.get('score_gmax', (S,))
+        gmax.copy_(state[:, 0])
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)
+        ops.score_rescale(state, gmax, d)
+        mine = self._reduce_scatter('score_state', state.view(W, B, 4 + 2 * d))          # [B, 4+2d]
+        loss_vec = ws.get('loss_vec', (B,))
+        lse_ny = ws.get('lse_ny', (B, 2))
+        grad_user = ws.get('grad_user', (B, d))
+        ops.score_finish(mine, gmax.view(W, B)[r], d, m.tau, n_pos, loss_vec, lse_ny, grad_user)
+        lse_all = self._all_gather('lse', lse_ny).view(S, 2)
+        dscore = ws.get('dscore_all', (S, N))
+        ops.score_dscore(z, ids_all, lab_all, lse_all, W, r, m.tau, m.SCORE_CLIP, n_pos, dscore)
+        # loss: local sum / global positives, then summed over ranks = global mean (reported value, not on the grad path)
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        ops.loss_finish(loss_vec, loss, denom_dev=n_pos, nan_flag=None)
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        self.nan_flag.copy_(torch.isnan(loss).to(torch.int32).view(1))
+        keys = ws.get('tgt_keys_local', (S * N,), dtype=torch.int32)
+        ops.shard_localize(ids_all, W, r, keys, pad_id=0)
+        self.last = dict(user=u_all, keys=keys, dscore=dscore, grad_user=grad_user, B=B, N=N, ids_all=ids_all, S=S)
+        scores = None
+        if want_scores:
+            zs = torch.where(ids_all % W == r, z, torch.zeros_like(z)).view(W, B, N)
+            scores = self._reduce_scatter('scores', zs.contiguous())
+            if m.SCORE_CLIP > 0:
+                scores = scores.clamp(-m.SCORE_CLIP, m.SCORE_CLIP)
+        return (loss if reduction else loss_vec.clone()), scores, user
+
+    def backward(self, grad_out=None):
+        st, m = self.last, self.model
+        d_user, dscore = st['grad_user'], st['dscore']
+        if grad_out is not None:
+            d_user = d_user * grad_out
+            dscore = dscore * grad_out
+        if m.has_item_bias:
+            self.flat.g('item_bias').index_add_(0, st['ids_all'].reshape(-1), dscore.reshape(-1))
+        if m.has_user_bias:
+            raise NotImplementedError('user_bias gradients with row-sharded tables')
+        self.rowgrad(self.table_for_target()).add(st['keys'], st['user'], st['N'], dscore, 1)
+        self.tower.backward(d_user)
+
+    def sync_dense_grads(self):
+        """Encoder gradients add across ranks (global normalisation): ONE all-reduce of the flat buffer."""
+        if self.flat is not None and self.flat.size:
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.group)
