@@ -1,0 +1,83 @@
+"""Worker for the row-sharded path (run under torch.distributed.run, one process per GPU, or with WORLD_SIZE=1).
+
+Every rank takes its slice of a golden fixture's batch, holds its shard of the golden tables, runs one fused step and
+checks: global loss == reference loss; after one step the re-assembled tables and the (replicated) encoder equal one
+step of the oracle's dense Adam (identical to lazy Adam on the first step)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+def main(name='sasrec_softmax'):
+    sys.argv = sys.argv[:1]
+    from golden_util import Golden, rel_err
+    from oracle import unirec_oracle as O
+    from unirec_b200 import sharding
+    from unirec_b200.facility.optim import FusedOptimizer
+    from unirec_b200.utils import argument_parser, general
+
+    W, r = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29533')
+        dist.init_process_group('nccl', rank=r, world_size=W)
+    g = Golden(name)
+    B = g.batch['item_id'].shape[0]
+    assert B % W == 0, (B, W)
+    args = dict(g.cfg)
+    args.update(exp_name='shard', dataset='example', table_shard_world=W, table_shard_rank=r, table_shard_force=True)
+    cfg = argument_parser.parse_arguments(args, argv=[])
+    cfg['device'] = dev
+    general.init_seed(2022)
+    model = general.get_class_instance(cfg['model'], 'unirec_b200/model')(cfg).to(dev)
+    sd = {k: v for k, v in g.params.items()}
+    sd['item_embedding.weight'] = sharding.shard_table(g.params['item_embedding.weight'], W, r)
+    model.load_state_dict(sd)
+    model.train()
+    model._ur_fast_grads = True
+    lr = float(cfg['learning_rate'])
+    opt = FusedOptimizer(model, 'adam', lr=lr)
+    sl = slice(r * (B // W), (r + 1) * (B // W))
+    batch = {k: v[sl].contiguous().to(dev) for k, v in g.fwd_batch().items()}
+    loss = model(**batch)[0]
+    opt.zero_grad()
+    loss.backward()
+    model._engine.sync_dense_grads()
+    opt.step()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(g.loss)) <= 1e-3 * abs(float(g.loss)), (float(loss), float(g.loss))
+    # oracle: one dense-Adam step on the full batch
+    p = {k: v.clone() for k, v in g.params.items()}
+    O.train_step(g.model, p, g.cfg, g.fwd_batch(), O.DenseAdam(p, lr=lr))
+    shards = [torch.empty_like(model.item_embedding.weight.data) if sharding.local_rows_count(g.cfg['n_items'], W, q) ==
+              model.item_embedding.weight.shape[0] else
+              torch.empty(sharding.local_rows_count(g.cfg['n_items'], W, q), model.item_embedding.weight.shape[1], device=dev)
+              for q in range(W)]
+    for q in range(W):
+        if q == r:
+            shards[q].copy_(model.item_embedding.weight.data)
+        dist.broadcast(shards[q], src=q)
+    table = sharding.unshard_tables([s.cpu() for s in shards])
+    err_t = rel_err(table, p['item_embedding.weight'])
+    worst = err_t
+    for k, v in model.state_dict().items():
+        if k == 'item_embedding.weight' or k.endswith('key.bias'):
+            continue
+        worst = max(worst, rel_err(v.cpu(), p[k]))
+    assert worst < 2e-3, worst
+    if r == 0:
+        print('SHARD_OK world=%d loss=%.6f ref=%.6f max_rel_err=%.2e' % (W, float(loss), float(g.loss), worst))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main(*sys.argv[1:])

@@ -1,0 +1,54 @@
+"""CPU (gloo, world_size 2): host-side logic of the row-sharded path -- ownership arithmetic, shard/unshard round trip, and
+the partial-softmax exchange protocol (all_reduce MAX of partial maxima, rescale, SUM) restated with torch CPU ops
+against the oracle's log-softmax.  The CUDA kernels themselves are covered by tests/test_gpu_sharded.py."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from unirec_b200 import sharding
+
+
+def test_shard_roundtrip_and_ownership():
+    full = torch.arange(23 * 4, dtype=torch.float32).view(23, 4)
+    for W in (1, 2, 3, 8):
+        shards = [sharding.shard_table(full, W, r) for r in range(W)]
+        assert [s.shape[0] for s in shards] == [sharding.local_rows_count(23, W, r) for r in range(W)]
+        assert torch.equal(sharding.unshard_tables(shards), full)
+        ids = torch.arange(23)
+        for r in range(W):
+            mine = ids[sharding.owner_of(ids, W) == r]
+            assert torch.equal(shards[r], full[mine]) and torch.equal(sharding.local_row(mine, W), torch.arange(len(mine)))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    V, d, B, N = 64, 8, 4, 9                      # every rank builds the same global problem
+    E, U = torch.randn(V, d, generator=g), torch.randn(world * B, d, generator=g)
+    ids = torch.randint(0, V, (world * B, N), generator=g)
+    s = (E[ids] * U[:, None, :]).sum(-1)
+    own = sharding.owner_of(ids, world) == rank
+    neg_inf = torch.full_like(s, float('-inf'))
+    s_own = torch.where(own, s, neg_inf)
+    m = s_own.max(1).values                                        # partial max (may be -inf: no owned entry)
+    l = torch.where(own, torch.exp(s - m[:, None]), torch.zeros_like(s)).sum(1)
+    l = torch.where(torch.isfinite(m), l, torch.zeros_like(l))
+    gm = m.clone()
+    dist.all_reduce(gm, op=dist.ReduceOp.MAX)                      # protocol step 1
+    scale = torch.where(l > 0, torch.exp(m - gm), torch.zeros_like(l))
+    l = l * scale                                                  # protocol step 2 (ur_score_rescale)
+    dist.all_reduce(l, op=dist.ReduceOp.SUM)                       # protocol step 3 (reduce_scatter in the product)
+    lse = gm + torch.log(l)
+    ref = torch.logsumexp(s, dim=1)
+    out[rank] = float((lse - ref).abs().max())
+    dist.destroy_process_group()
+
+
+def test_partial_softmax_protocol_gloo_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, 29711, out), nprocs=2, join=True)
+    assert len(out) == 2 and max(out.values()) < 1e-5, dict(out)

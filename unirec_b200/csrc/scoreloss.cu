@@ -286,11 +286,18 @@ __global__ void __launch_bounds__(1024) loss_finish_kernel(const float* __restri
     }
 }
 
+// out (pre-zeroed) += number of positive labels; per-CTA integer partials, one float atomic each (exact below 2^24)
 __global__ void __launch_bounds__(256) count_positive_kernel(const int32_t* __restrict__ label, int64_t n, float* out) {
-    // single CTA; labels are tiny next to the table rows
     __shared__ int sh[8];
     int c = 0;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) c += label[i] > 0;
+    const int64_t n4 = n >> 2;
+    const int4* l4 = reinterpret_cast<const int4*>(label);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 v = __ldg(l4 + i);
+        c += (v.x > 0) + (v.y > 0) + (v.z > 0) + (v.w > 0);
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) c += label[i] > 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(256) count_positive_kernel(const int32_t* __re
     if (threadIdx.x == 0) {
         int t = 0;
         for (int i = 0; i < 8; ++i) t += sh[i];
-        *out = (float)t;
+        if (t) atomicAdd(out, (float)t);
     }
 }
 
@@ -327,7 +334,13 @@ static int launch_score_loss(const ScoreLossParams& p, int loss_type, size_t sme
 extern "C" {
 
 int ur_count_positive_i32(const int32_t* label, int64_t n, float* out, void* stream) {
-    ur::count_positive_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(label, n, out);
+    if (reinterpret_cast<uintptr_t>(label) & 15) return UR_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(out, 0, sizeof(float), st);
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > ur::kNumSMs * 4) blocks = ur::kNumSMs * 4;
+    if (blocks < 1) blocks = 1;
+    ur::count_positive_kernel<<<(unsigned)blocks, 256, 0, st>>>(label, n, out);
     UR_RETURN_LAST_ERROR();
 }
 

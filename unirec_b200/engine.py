@@ -162,6 +162,9 @@ class SASRecTower:
         self.eps = float(cfg['layer_norm_eps'])
         self.causal = bool(cfg['use_position_emb'])
         self.dh = self.d // self.H
+        if float(cfg.get('hidden_dropout_prob', 0) or 0) > 0 or float(cfg.get('attn_dropout_prob', 0) or 0) > 0:
+            raise ValueError('unirec_b200: dropout > 0 is not implemented in the fused encoder yet; set '
+                             'hidden_dropout_prob=0 and attn_dropout_prob=0 (ignoring it silently would change training)')
 
     @staticmethod
     def flat_order(model):
@@ -272,6 +275,8 @@ class GRUTower:
         self.eng = eng
         self.d = int(cfg['embedding_size'])
         self.Hd = int(cfg.get('hidden_size', self.d))
+        if float(cfg.get('dropout_prob', 0) or 0) > 0:
+            raise ValueError('unirec_b200: dropout_prob > 0 is not implemented in the fused GRU tower yet')
 
     @staticmethod
     def flat_order(model):

@@ -113,7 +113,11 @@ class Trainer(object):
         """Multi-process: the encoder is replicated, its flat gradient buffer is averaged with ONE all-reduce
         (replaces DDP's bucketed all-reduce of every parameter incl. whole tables)."""
         if self.accelerator.distributed:
-            flat = self.accelerator.unwrap_model(self.model)._engine.flat
+            eng = self.accelerator.unwrap_model(self.model)._engine
+            if hasattr(eng, 'sync_dense_grads'):
+                eng.sync_dense_grads()        # sharded tables: loss normalised globally, gradients add
+                return
+            flat = eng.flat
             if flat is not None and flat.size:
                 dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
                 flat.grad.div_(self.accelerator.num_processes)

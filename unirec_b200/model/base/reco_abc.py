@@ -4,6 +4,7 @@ Parameter creation stays in torch, in the reference's order, so seeds reproduce 
 bit for bit; everything numerical afterwards runs in the CUDA engine.
 """
 import logging
+import os
 
 import torch
 import torch.nn as nn
@@ -104,6 +105,9 @@ class AbstractRecommender(nn.Module):
         self.has_user_bias = bool(config.get('has_user_bias', False))
         self.has_item_bias = bool(config.get('has_item_bias', False))
         self.tau = config.get('tau', 1.0)
+        # unirec_b200 addition: row-sharding of the item tables over the ranks of one box (see unirec_b200/sharding.py)
+        self.shard_world = int(config.get('table_shard_world', 1) or 1)
+        self.shard_rank = int(config.get('table_shard_rank', os.environ.get('RANK', 0))) if self.shard_world > 1 else 0
 
     def _init_modules(self):
         # creation order is part of the RNG contract (reference reco_abc.py:159-189)
@@ -113,7 +117,10 @@ class AbstractRecommender(nn.Module):
             self.item_bias = nn.Parameter(torch.normal(0, 0.1, size=(self.n_items,)))
         if self.config['has_user_emb']:
             self.user_embedding = nn.Embedding(self.n_users, self.embedding_size, padding_idx=0)
-        self.item_embedding = nn.Embedding(self.n_items, self.embedding_size, padding_idx=0)
+        # row-sharded item tables (multi-GPU): this rank stores rows {id : id % W == r}; the padding row lives on rank 0
+        W, r = self.shard_world, self.shard_rank
+        rows = (self.n_items - r + W - 1) // W
+        self.item_embedding = nn.Embedding(rows, self.embedding_size, padding_idx=0 if r == 0 else None)
         self._define_model_layers()
         self._init_params()
 

@@ -80,7 +80,11 @@ class BaseRecommender(AbstractRecommender):
                                  % scorer_type)
             raise ValueError('not supported distance_type: {0}'.format(scorer_type))
         super()._init_modules()
-        self._engine = Engine(self, self._tower_kind)
+        if self.shard_world > 1 or self.config.get('table_shard_force', False):
+            from unirec_b200.sharding import ShardedEngine
+            self._engine = ShardedEngine(self, self._tower_kind, self.shard_world, self.shard_rank)
+        else:
+            self._engine = Engine(self, self._tower_kind)
         self._ur_fast_grads = False
 
     def _define_model_layers(self):
