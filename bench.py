@@ -182,7 +182,8 @@ def main():
         trainer.train_step(resident[i % n_pool])
     barrier()
     ops.LAUNCH_COUNT = 0
-    ops.TIMED_OP, ops.TIMED_EVENTS = 'ur_score_loss_fwd_bwd_f32', []
+    # sharded tables (N>1): the owner-side partial-softmax kernel is the row-gather kernel (same rows per rank per step)
+    ops.TIMED_OP, ops.TIMED_EVENTS = ('ur_score_loss_fwd_bwd_f32' if world == 1 else 'ur_score_partial_f32'), []
     clocks = ClockSampler(dev.index or 0)
     clocks.start()
     barrier()
@@ -248,7 +249,8 @@ def main():
         'e2e': {'value': samples / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'score_loss_kernel (fused gather+dot+softmax+grad)', 'bound': 'hbm', 'achieved': achieved,
+        'roofline': {'kernel': 'score_loss_kernel (fused gather+dot+softmax+grad)' if world == 1 else
+                     'score_partial_kernel (owner-side gather+dot+partial softmax, row-sharded table)', 'bound': 'hbm', 'achieved': achieved,
                      'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None, 'peak_kind': peak_kind,
                      'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': k_ms},
         'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
