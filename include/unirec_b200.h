@@ -74,6 +74,14 @@ int ur_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const f
 int ur_gemm_simt_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                      int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
                      void* stream);
+/* tcgen05 / TMEM / TMA kernel behind ur_gemm_f32 (csrc/gemm_tc.cu): TF32 operands read in place from fp32, fp32 accumulate.
+ * Supports NT (A [M,K], B [N,K]) and TN (A stored [K,M], B stored [K,N], split-K with atomic accumulate) when N % 128 == 0 and
+ * K % 32 == 0; returns UR_ERR_UNSUPPORTED otherwise. */
+int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                   int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
+                   int precision, void* stream);
+/* out[c][r] = in[r][c] for small weight matrices (dx = dy W is issued as an NT product on W^T) */
+int ur_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
 /* dY *= act'(preact) */
 int ur_act_bwd_f32(float* dY, const float* preact, int64_t n, int act, void* stream);
 /* out[n] += sum_m X[m,n] (bias gradients) */

@@ -345,3 +345,45 @@ def test_gru_gates_fwd_bwd():
     dgi, dgh, dhp = torch.empty(B, 3 * H, device=DEV), torch.empty(B, 3 * H, device=DEV), torch.empty(B, H, device=DEV)
     ops.gru_gate_bwd(dh.to(DEV), save, hp.to(DEV), dgi, 3 * H, dgh, dhp, B, H)
     assert rel(dgi, gir.grad) < 1e-4 and rel(dgh, ghr.grad) < 1e-4 and rel(dhp, hpr.grad) < 1e-4
+
+
+# ---------------------------------------------------------------- tcgen05 tensor-core GEMM (TF32 in, fp32 accumulate)
+TF32_TOL = 2e-3     # TF32 keeps 10 mantissa bits: ~5e-4 per product, bar for the tf32 mode is 1e-2 (bf16-class) / measured ~3e-4
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 128, 128), (1000, 384, 128), (777, 512, 512), (128, 256, 64), (5000, 128, 512)])
+@pytest.mark.parametrize('act', [None, 'swish'])
+def test_gemm_tc_nt(M, N, K, act):
+    from unirec_b200 import ops
+    assert ops.has_tensor_core_gemm()
+    g = gen(21)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.1, torch.randn(N, generator=g)
+    C, pre = torch.full((M, N), 7.0, device=DEV), torch.empty(M, N, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), C, M, N, K, transB=True, bias=b.to(DEV), act=act, preact=pre, precision=1)
+    ref_pre = O.linear(A.double(), W.double(), b.double())
+    ref = O.activation(ref_pre, act) if act else ref_pre
+    assert rel(pre, ref_pre) < TF32_TOL and rel(C, ref) < TF32_TOL
+    # accumulate (read-add-store epilogue)
+    C2 = torch.ones(M, N, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), C2, M, N, K, transB=True, accumulate=True, precision=1)
+    assert rel(C2, 1.0 + A.double() @ W.double().t()) < TF32_TOL
+
+
+@pytest.mark.parametrize('Mo,No,T', [(128, 128, 5024), (384, 128, 51200), (512, 128, 4096), (128, 512, 4096)])
+def test_gemm_tc_tn_weight_grad(Mo, No, T):
+    """dW[Mo,No] += dY[T,Mo]^T @ X[T,No]: both operands MN-major, split-K over the token dimension."""
+    from unirec_b200 import ops
+    g = gen(22)
+    dY, X = torch.randn(T, Mo, generator=g), torch.randn(T, No, generator=g)
+    dW = torch.zeros(Mo, No, device=DEV)
+    ops.gemm(dY.to(DEV), X.to(DEV), dW, Mo, No, T, transA=True, lda=Mo, accumulate=True, precision=1)
+    ref = dY.double().t() @ X.double()
+    assert rel(dW, ref) < TF32_TOL
+
+
+def test_transpose_small():
+    from unirec_b200 import ops
+    w = torch.randn(384, 128, generator=gen(23))
+    out = torch.empty(128, 384, device=DEV)
+    ops.transpose(w.to(DEV), out)
+    assert torch.equal(out.cpu(), w.t().contiguous())

@@ -24,6 +24,8 @@ SIGNATURES = {
     'ur_add_ln_bwd_f32': 'plppp' + 'pl' + 'pl' + 'li' + 'pl' + 'ppp',
     'ur_gemm_f32': 'iilllplplplpipliip',
     'ur_gemm_simt_f32': 'iilllplplplpiplip',
+    'ur_gemm_tc_f32': 'iilllplplplpipliip',
+    'ur_transpose_f32': 'pllpp',
     'ur_act_bwd_f32': 'pplip',
     'ur_colsum_accum_f32': 'plllpp',
     'ur_attn_fwd_f32': 'ppliiiiippp',

@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
 // Backward: one CTA per (sample, head).  Query rows are processed in tiles of QT; phase A (warp per query row)
 // recomputes P, forms dS and writes dQ; phase B (warp per key, exclusive ownership -> no atomics) accumulates
 // dK and dV in registers across all tiles.
-template <int DH, int KPW>   // KPW = max keys owned per warp = ceil(L / 8)
-__global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq, int L, int H,
+template <int DH, int KPW>   // KPW = max keys owned per warp = ceil(L / 8); register cap scales with it
+__global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) attn_bwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq, int L, int H,
                                                           float scale, int causal, int q_only_last, const float* __restrict__ ctx,
                                                           const float* __restrict__ lse, const float* __restrict__ dctx,
                                                           float* __restrict__ dqkv) {

@@ -60,7 +60,7 @@ struct OptHyper {
 };
 
 template <int D4>
-__global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* __restrict__ table, float4* __restrict__ mom, float4* __restrict__ var,
+__global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float4* mom, float4* var,
                                                             int32_t* __restrict__ head, const int32_t* __restrict__ next,
                                                             const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq,
                                                             RowSource s0, int32_t n0, RowSource s1, int mode, OptHyper h,
@@ -81,12 +81,25 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* __restrict__
         bc2s = sqrtf(1.f - powf(h.beta2, t));
     }
     float sq = 0.f;
+    const bool is_adam = (mode == OPT_ADAM || mode == OPT_ADAMW);
+    const bool update = (mode != OPT_SQNORM) && !skip;
     for (int64_t u = group0; u < nu; u += ngroups) {
         const int64_t id = uniq[u];
+        int32_t e = head[id];
+        // Issue the parameter / moment loads FIRST: they do not depend on the list walk, so their HBM latency overlaps
+        // the dependent chain head -> entry -> source row below.
+        float4 P[VPL], M[VPL], W[VPL];
+        if (update) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int64_t o = id * D4 + v * LPR + col;
+                P[v] = ld_stream_rw(table + o);
+                if (is_adam) { M[v] = ld_stream_rw(mom + o); W[v] = ld_stream_rw(var + o); }
+            }
+        }
         float4 g[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int32_t e = head[id];
         while (e >= 0) {
             const bool first = e < n0;
             const RowSource& s = first ? s0 : s1;
@@ -108,15 +121,15 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* __restrict__
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             const int64_t o = id * D4 + v * LPR + col;
-            float4 p = table[o];
+            float4 p = P[v];
             float4 gg = f4_scale(g[v], gs);
             if (mode == OPT_SGD) {
                 if (h.weight_decay != 0.f) gg = f4_fma(h.weight_decay, p, gg);
-                table[o] = f4_fma(-h.lr, gg, p);
+                stg_stream(table + o, f4_fma(-h.lr, gg, p));
             } else {
                 if (mode == OPT_ADAM && h.weight_decay != 0.f) gg = f4_fma(h.weight_decay, p, gg);
                 if (mode == OPT_ADAMW && h.weight_decay != 0.f) p = f4_scale(p, 1.f - h.lr * h.weight_decay);
-                float4 m = mom[o], w = var[o];
+                float4 m = M[v], w = W[v];
                 const float o1 = 1.f - h.beta1, o2 = 1.f - h.beta2;
                 m.x = h.beta1 * m.x + o1 * gg.x; m.y = h.beta1 * m.y + o1 * gg.y;
                 m.z = h.beta1 * m.z + o1 * gg.z; m.w = h.beta1 * m.w + o1 * gg.w;
@@ -125,7 +138,7 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* __restrict__
                 const float a = h.lr / bc1;
                 p.x -= a * m.x / (sqrtf(w.x) / bc2s + h.eps); p.y -= a * m.y / (sqrtf(w.y) / bc2s + h.eps);
                 p.z -= a * m.z / (sqrtf(w.z) / bc2s + h.eps); p.w -= a * m.w / (sqrtf(w.w) / bc2s + h.eps);
-                mom[o] = m; var[o] = w; table[o] = p;
+                stg_stream(mom + o, m); stg_stream(var + o, w); stg_stream(table + o, p);
             }
         }
     }

@@ -136,10 +136,20 @@ def _lin_fwd(x, M, K, w, b, N, out, act=None, preact=None, lda=None, prec=0):
     return ops.gemm(x, w, out, M, N, K, transB=True, lda=lda, bias=b, act=act, preact=preact, precision=prec)
 
 
+_WT_WS = None      # workspace holding transposed weight copies for the tensor-core dx path (set by Engine.ensure_ready)
+
+
 def _lin_bwd(dy, M, N, x, K, w, dx, dw, db, lda_x=None, accumulate_dx=False, prec=0, lddy=None, lddx=None):
     """y = x w^T + b.  dx[M,K] (+)= dy[M,N] @ w[N,K];  dw[N,K] += dy^T x;  db[N] += colsum(dy)."""
+    wt_ws = _WT_WS
     if dx is not None:
-        ops.gemm(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec)
+        if prec != 0 and wt_ws is not None and K % 128 == 0 and N % 32 == 0:
+            # tensor-core path: dx = dy @ w is issued as an NT product on W^T (both operands K-major for tcgen05)
+            wt = wt_ws.get('wT_%dx%d' % (K, N), (K, N))
+            ops.transpose(w.view(N, K), wt)
+            ops.gemm(dy, wt, dx, M, K, N, transB=True, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec)
+        else:
+            ops.gemm(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec)
     ops.gemm(dy, x, dw, N, K, M, transA=True, lda=lddy or N, ldb=lda_x, accumulate=True, precision=prec)
     if db is not None:
         ops.colsum_accum(dy, M, N, db, ldx=lddy)
@@ -441,6 +451,8 @@ class Engine:
             if not p.data.is_contiguous():
                 p.data = p.data.contiguous()
         self.ws = Workspace(dev)
+        global _WT_WS
+        _WT_WS = self.ws
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._rowgrads = {}
 

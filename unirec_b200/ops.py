@@ -148,6 +148,13 @@ def gemm(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None, ldc=N
     return C
 
 
+def transpose(w, out):
+    """out[c, r] = w[r, c] (small weight matrices)."""
+    rows, cols = w.shape
+    _call('ur_transpose_f32', _f32(w), rows, cols, _f32(out), _stream())
+    return out
+
+
 def act_bwd(dY, preact, act):
     _call('ur_act_bwd_f32', _f32(dY), _f32(preact), dY.numel(), ACT_CODES[act], _stream())
     return dY
