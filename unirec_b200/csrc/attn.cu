@@ -33,18 +33,41 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
         *reinterpret_cast<float4*>(Ks + j * KS + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + d + c));
         *reinterpret_cast<float4*>(Vs + j * KS + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + 2 * d + c));
     }
-    for (int j = threadIdx.x; j < L; j += blockDim.x) madd[j] = seq[(int64_t)b * L + j] > 0 ? 0.f : kMaskAdd;
+    __shared__ int s_jlo;
+    if (threadIdx.x == 0) s_jlo = L;
     __syncthreads();
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const bool valid = seq[(int64_t)b * L + j] > 0;
+        madd[j] = valid ? 0.f : kMaskAdd;
+        if (valid) atomicMin(&s_jlo, j);
+    }
+    __syncthreads();
+    // Exact work skipping (results identical to the dense reference computation):
+    //  * a padded QUERY row never reaches the loss (only real positions feed the last position through unmasked keys), so its
+    //    context is written as zeros instead of a softmax over all-masked keys;
+    //  * for a real query row at least one key is unmasked, hence every masked key has weight exp(-10000 + ...) == 0 in fp32:
+    //    keys before the first real item and (causal) keys after the query are skipped.
+    const int j_lo = s_jlo;
 
     const int q_begin = q_only_last ? L - 1 : blockIdx.y * q_tile;
     const int q_end = q_only_last ? L : min(L, q_begin + q_tile);
     float* pw = pbuf + warp * Lp;
     float* qw = qbuf + warp * DH;
     for (int i = q_begin + warp; i < q_end; i += 8) {
+        if (madd[i] != 0.f) {                       // padded query row: dead output, keep it finite
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                const int c = lane + 32 * r;
+                if (c < DH) ctx[((int64_t)b * L + i) * d + h * DH + c] = 0.f;
+            }
+            if (lane == 0) lse[((int64_t)b * H + h) * L + i] = 0.f;
+            continue;
+        }
+        const int j_hi = causal ? i : L - 1;        // inclusive
         for (int c = lane; c < DH; c += 32) qw[c] = __ldg(base + (int64_t)i * 3 * d + c);
         __syncwarp();
         float mx = -INFINITY;
-        for (int j = lane; j < L; j += 32) {
+        for (int j = j_lo + lane; j <= j_hi; j += 32) {
             float dot = 0.f;
 #pragma unroll
             for (int c = 0; c < DH; c += 4) {
@@ -52,14 +75,13 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
                 const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * KS + c);
                 dot += f4_dot(q4, k4);
             }
-            const float add = (causal && j > i) ? kMaskAdd : madd[j];
-            const float s = dot * scale + add;
+            const float s = dot * scale + madd[j];
             pw[j] = s;
             mx = fmaxf(mx, s);
         }
         mx = warp_max(mx);
         float sum = 0.f;
-        for (int j = lane; j < L; j += 32) {
+        for (int j = j_lo + lane; j <= j_hi; j += 32) {
             const float p = __expf(pw[j] - mx);
             pw[j] = p;
             sum += p;
@@ -69,7 +91,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
         float o[CPL];
 #pragma unroll
         for (int r = 0; r < CPL; ++r) o[r] = 0.f;
-        for (int j = 0; j < L; ++j) {
+        for (int j = j_lo; j <= j_hi; ++j) {
             const float p = pw[j];
 #pragma unroll
             for (int r = 0; r < CPL; ++r) {
@@ -119,7 +141,14 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
         *reinterpret_cast<float4*>(Ks + j * KS + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + d + c));
         *reinterpret_cast<float4*>(Vs + j * KS + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + 2 * d + c));
     }
-    for (int j = threadIdx.x; j < L; j += blockDim.x) madd[j] = seq[(int64_t)b * L + j] > 0 ? 0.f : kMaskAdd;
+    __shared__ int s_jlo;
+    if (threadIdx.x == 0) s_jlo = L;
+    __syncthreads();
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const bool valid = seq[(int64_t)b * L + j] > 0;
+        madd[j] = valid ? 0.f : kMaskAdd;
+        if (valid) atomicMin(&s_jlo, j);
+    }
 
     float dKr[KPW][CPL], dVr[KPW][CPL];
 #pragma unroll
@@ -138,15 +167,26 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
             *reinterpret_cast<float4*>(dOs + ii * DH + c) = __ldg(reinterpret_cast<const float4*>(dctx + row * d + h * DH + c));
         }
         __syncthreads();
-        // ---- phase A ----
+        // ---- phase A ----  (same exact skipping as the forward kernel: padded query rows have dctx == 0 and contribute
+        //                     nothing; masked keys have P == 0 for real query rows)
+        const int j_lo = s_jlo;
         for (int ii = warp; ii < nq; ii += 8) {
             const int i = q0 + ii;
+            if (madd[i] != 0.f) {                      // padded query row: dQ = 0, no dK/dV contribution
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) {
+                    const int c = lane + 32 * r;
+                    if (c < DH) dbase[(int64_t)i * 3 * d + c] = 0.f;
+                }
+                continue;
+            }
+            const int j_hi = causal ? i : L - 1;
             const int64_t row = (int64_t)b * L + i;
             float dsum = 0.f;
             for (int c = lane; c < DH; c += 32) dsum = fmaf(dOs[ii * DH + c], __ldg(ctx + row * d + h * DH + c), dsum);
             const float Di = warp_sum(dsum);
             const float lse_i = lse[((int64_t)b * H + h) * L + i];
-            for (int j = lane; j < L; j += 32) {
+            for (int j = j_lo + lane; j <= j_hi; j += 32) {
                 float dot = 0.f, dp = 0.f;
 #pragma unroll
                 for (int c = 0; c < DH; c += 4) {
@@ -157,8 +197,7 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
                     dot += f4_dot(q4, k4);
                     dp += f4_dot(g4, v4);
                 }
-                const float add = (causal && j > i) ? kMaskAdd : madd[j];
-                const float p = __expf(dot * scale + add - lse_i);
+                const float p = __expf(dot * scale + madd[j] - lse_i);
                 Ps[ii * Lp + j] = p;
                 dSs[ii * Lp + j] = p * (dp - Di) * scale;
             }
@@ -166,7 +205,7 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
             float dq[CPL];
 #pragma unroll
             for (int r = 0; r < CPL; ++r) dq[r] = 0.f;
-            for (int j = 0; j < L; ++j) {
+            for (int j = j_lo; j <= j_hi; ++j) {
                 const float ds = dSs[ii * Lp + j];
 #pragma unroll
                 for (int r = 0; r < CPL; ++r) {
@@ -185,8 +224,10 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
 #pragma unroll
         for (int k = 0; k < KPW; ++k) {
             const int j = warp + 8 * k;
-            if (j < L) {
-                for (int ii = 0; ii < nq; ++ii) {
+            if (j < L && j >= j_lo) {
+                // rows that wrote P/dS for this key: real query rows, and (causal) only rows i >= j
+                for (int ii = causal ? max(0, j - q0) : 0; ii < nq; ++ii) {
+                    if (madd[q0 + ii] != 0.f) continue;
                     const float ds = dSs[ii * Lp + j], p = Ps[ii * Lp + j];
 #pragma unroll
                     for (int r = 0; r < CPL; ++r) {

@@ -92,6 +92,15 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
         default: return x;
     }
 }
+// fast-intrinsic variant for the reduced-precision (TF32/BF16) GEMM epilogues: ~6 instructions instead of ~40 per element
+__device__ __forceinline__ float act_fwd_fast(float x, int act) {
+    switch (act) {
+        case ACT_SWISH: return __fdividef(x, 1.f + __expf(-x));
+        case ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-x));
+        case ACT_RELU: return fmaxf(x, 0.f);
+        default: return act_fwd(x, act);
+    }
+}
 // derivative of the activation at pre-activation x
 __device__ __forceinline__ float act_bwd(float x, int act) {
     switch (act) {

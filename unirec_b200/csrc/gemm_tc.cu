@@ -19,7 +19,8 @@ namespace tc {
 
 constexpr int BM = 128;          // rows of C per CTA (UMMA M)
 constexpr int BK = 32;           // fp32 elements per k-block = 128 bytes = one swizzle span
-constexpr int MAX_NC = 512;      // columns of C per CTA (TMEM columns)
+constexpr int MAX_NC = 256;      // columns of C per CTA: 256 TMEM columns and <= 100 KB smem -> 2 CTAs per SM, so one CTA's
+                                 // epilogue overlaps the other's TMA/MMA main loop (the A stripe is re-read from L2 per chunk)
 constexpr int NUM_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,7 +104,7 @@ struct Params {
 static int g_dbg_lbo = 32 * BK * 4, g_dbg_sbo = 512, g_dbg_kstep = 1024, g_dbg_major = 1, g_dbg_layout = 1, g_dbg_tma_swz = 4;
 
 template <bool kTN>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     uint64_t* empty = full + S;
     uint64_t* tmem_full = empty + S;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NC;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * NC;      // column chunks of one A stripe are adjacent in launch order
     const int KB_all = (p.K + BK - 1) / BK;
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int KB = min(KB_all - kb_begin, p.kb_per_split);     // k-blocks of this CTA (>= 1 by construction)
@@ -201,7 +202,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const int ncol = n0 + c0;
             if (p.bias && blockIdx.z == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + ncol + i);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + i));
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
             }
             for (int pass = 0; pass < 2; ++pass) {
                 float* out = pass == 0 ? p.preact : p.C;
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 if (out == nullptr) continue;
                 if (pass == 1 && p.act != ACT_NONE) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = act_fwd(v[i], p.act);
+                    for (int i = 0; i < 32; ++i) v[i] = act_fwd_fast(v[i], p.act);
                 }
                 __syncwarp();
 #pragma unroll
@@ -316,7 +320,7 @@ int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
         if (N % c == 0) { NC = c; break; }
     if (!NC) return UR_ERR_UNSUPPORTED;
     const uint32_t stage_bytes = BM * BK * 4 + (uint32_t)NC * BK * 4;
-    int stages = (int)((200 * 1024) / stage_bytes);
+    int stages = (int)((100 * 1024) / stage_bytes);      // two CTAs per SM
     const int KB = (int)(K / BK);
     // split-K along the reduction (token) dimension when the output has too few tiles to fill the GPU (weight gradients)
     const int64_t tiles = ((M + BM - 1) / BM) * (N / NC);
@@ -346,7 +350,7 @@ int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
     p.tmem_cols = NC <= 128 ? 128 : (NC <= 256 ? 256 : 512);
     p.kb_per_split = kb_per_split;
     p.dbg_lbo = g_dbg_lbo; p.dbg_sbo = g_dbg_sbo; p.dbg_kstep = g_dbg_kstep; p.dbg_major = g_dbg_major; p.dbg_layout = g_dbg_layout;
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)(N / NC), (unsigned)splits);
+    dim3 grid((unsigned)(N / NC), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
     cudaStream_t st = (cudaStream_t)stream;
     if (nt) {
         cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
