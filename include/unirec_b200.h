@@ -133,6 +133,17 @@ int ur_sqnorm_accum_f32(const float* grad, int64_t n, float* sqnorm, void* strea
 int ur_clip_coef_f32(const float* sqnorm, float max_norm, float* coef, void* stream);
 int ur_step_advance(int32_t* step, const int32_t* skip_flag, void* stream);
 
+/* ---- a15 / f1: device-side batch builder: (user, positive) pairs + CSR user history -> the batch contract
+ * (item_id [B,1+K] positive first, label [B,1+K], item_seq [B,L] left-padded, item_seq_len [B]).
+ * replaces: AddNegSamples.__call__ unirec/data/transform/addnegsamples.py:90-115 (uniform or popularity-alias draws, <=100 retries,
+ *           reject the positive and the user's history, id 0 on failure); AddUserHistory.__call__ adduserhistory.py:32-73
+ *           (mask_mode 1 = unorder, 2 = autoregressive, seq_last); SeqRecDataset._padding seqrecdataset.py:60-68.
+ * hist_* / alias_* / item_seq are nullable (L = 0: no history columns). */
+int ur_build_batch(const int64_t* user_id, const int64_t* pos_item, int64_t B, const int64_t* hist_ptr, const int32_t* hist_items,
+                   const int32_t* hist_sorted, int64_t n_users, int64_t n_items, const float* alias_prob, const int32_t* alias_idx,
+                   int K, int L, int mask_mode, int seq_last, int64_t seed, int64_t step, int64_t* item_id, int32_t* label,
+                   int32_t* item_seq, int64_t* item_seq_len, void* stream);
+
 /* ---- Row-sharded tables (multi-GPU): rank r of `world` owns rows {id : id % world == r} at local index id / world.
  * These replace the reference's replicated tables + DDP all-reduce of dense [V,d] gradients
  * (unirec/model/base/reco_abc.py:167-170, unirec/facility/trainer.py:67,346) together with NCCL collectives issued by the host

@@ -41,6 +41,7 @@ SIGNATURES = {
     'ur_sqnorm_accum_f32': 'plpp',
     'ur_clip_coef_f32': 'pfpp',
     'ur_step_advance': 'ppp',
+    'ur_build_batch': 'pplppp' + 'llpp' + 'iiii' + 'll' + 'pppp' + 'p',
     'ur_shard_gather_rows_f32': 'pipiliipp',
     'ur_shard_localize': 'piliilpp',
     'ur_score_partial_f32': 'pippli' + 'pppp' + 'ffii' + 'ppp',

@@ -252,6 +252,29 @@ def step_advance(step, skip_flag=None):
           _stream())
 
 
+# ------------------------------------------------------------------ device-side batch builder
+MASK_MODES = {None: 0, 'none': 0, 'unorder': 1, 'autoregressive': 2}
+
+
+def build_batch(user_id, pos_item, n_users, n_items, K, L, hist_ptr=None, hist_items=None, hist_sorted=None, alias_prob=None,
+                alias_idx=None, mask_mode='unorder', seq_last=0, seed=0, step=0):
+    """Returns (item_id [B,1+K] i64, label [B,1+K] i32, item_seq [B,L] i32 | None, item_seq_len [B] i64 | None)."""
+    B = user_id.shape[0]
+    dev = user_id.device
+    item_id = torch.empty(B, 1 + K, dtype=torch.int64, device=dev)
+    label = torch.empty(B, 1 + K, dtype=torch.int32, device=dev)
+    item_seq = torch.empty(B, L, dtype=torch.int32, device=dev) if L > 0 else None
+    seq_len = torch.empty(B, dtype=torch.int64, device=dev) if L > 0 else None
+    _call('ur_build_batch', _ptr(user_id, torch.int64), _ptr(pos_item, torch.int64), B,
+          _ptr(hist_ptr, torch.int64) if hist_ptr is not None else None,
+          _ptr(hist_items, torch.int32) if hist_items is not None else None,
+          _ptr(hist_sorted, torch.int32) if hist_sorted is not None else None, n_users, n_items, _f32(alias_prob),
+          _ptr(alias_idx, torch.int32) if alias_idx is not None else None, K, L, MASK_MODES.get(mask_mode, 0), int(seq_last),
+          int(seed) & 0x7FFFFFFFFFFFFFFF, int(step), _ptr(item_id), _ptr(label), _ptr(item_seq) if item_seq is not None else None,
+          _ptr(seq_len) if seq_len is not None else None, _stream())
+    return item_id, label, item_seq, seq_len
+
+
 # ------------------------------------------------------------------ row-sharded tables (multi-GPU)
 def shard_gather_rows(table_local, idx, world, rank, out):
     _call('ur_shard_gather_rows_f32', _f32(table_local), table_local.shape[1], _ptr(idx), _idx_bits(idx), idx.numel(), world,

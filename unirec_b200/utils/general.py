@@ -67,3 +67,27 @@ def load_model_freely(filename, device=None):
     model = get_class_instance(cfg['model'], 'unirec_b200/model')(cfg).to(device)
     model.load_state_dict(cpt['state_dict'], strict=False)
     return model, cfg
+
+
+def load_user_history(file_path, file_name, n_users=None, format='user-item', time_seq=0):
+    """User histories as the reference returns them (general.py:111-149): an object ndarray indexed by user id whose entries are
+    per-user item arrays (None for users without history), plus the time histories (not supported here -> None).
+    `unirec_b200.data.history.UserHistoryCSR.from_object_array` turns it into the CSR form the device path uses."""
+    import pandas as pd
+    from unirec_b200.constants.protocols import ColNames, DataFileFormat
+    from unirec_b200.data.dataset.basedataset import load_frame
+    if time_seq:
+        raise ValueError('time sequences are outside the accelerated path')
+    df = load_frame(file_path, file_name)
+    if format in (DataFileFormat.T1.value, DataFileFormat.T3.value):
+        grouped = df.groupby('user_id')['item_id'].apply(lambda x: np.array(x))
+    elif format in (DataFileFormat.T5.value, DataFileFormat.T6.value):
+        grouped = df.set_index('user_id')[ColNames.USER_HISTORY.value].to_dict()
+    else:
+        raise NotImplementedError('Unsupport user history format: {0}'.format(format))
+    if n_users is None or n_users <= 0:
+        n_users = int(df['user_id'].max()) + 1
+    res = np.empty(n_users, dtype=object)
+    for user_id, items in grouped.items():
+        res[user_id] = np.asarray(items)
+    return res, None
