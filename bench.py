@@ -130,7 +130,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=None)
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--gemm-precision', default='fp32', choices=['fp32', 'tf32', 'bf16'])
+    ap.add_argument('--gemm-precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     sys.argv = sys.argv[:1]
@@ -240,7 +240,7 @@ def main():
     line = {
         'metric': 'training samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32' if args.gemm_precision == 'fp32' else args.gemm_precision, 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': 'tf32' if args.gemm_precision == 'tf32' else 'f32', 'data': 'synthetic',
         'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'seq_len': L, 'n_items': w['n_items'],
                    'n_neg': K, 'optimizer': 'adam: row-sparse (lazy) on tables, flat dense on encoder', 'dropout': 0.0,
                    'gemm_precision': args.gemm_precision, 'l2': 'inputs larger than L2: %.1f GB table, random rows, %d rotating batches'

@@ -59,15 +59,17 @@ int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* ga
  * replaces: LayerNorm(hidden + input) unirec/model/modules.py:314, :353 */
 int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R /*nullable*/, int64_t ldr, const float* gamma, const float* beta,
                       float eps, int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd, void* stream);
-/* dZ = LN'(Z) (dY + dExtra); dgamma/dbeta ACCUMULATED; dZ may alias dY */
+/* dZ = LN'(Z) (dY + dExtra); dgamma/dbeta ACCUMULATED; dZ may alias dY; dzsum (nullable) += column sums of dZ, i.e. the
+ * bias gradient of the linear layer whose output (plus residual) is Z */
 int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const float* mean, const float* rstd, const float* dY,
                       int64_t lddy, const float* dExtra /*nullable*/, int64_t ldde, int64_t rows, int d, float* dZ, int64_t lddz,
-                      float* dgamma, float* dbeta, void* stream);
+                      float* dgamma, float* dbeta, float* dzsum /*nullable*/, void* stream);
 
 /* ---- K4/K7: C (+)= act(op(A) op(B) + bias); preact (nullable) receives the pre-activation for backward.
  * replaces: nn.Linear calls unirec/model/modules.py:285-287,312,348-351; gru.py:30-31
  * ur_gemm_f32 picks the tcgen05 tensor-core kernel when the shape qualifies and precision != 0, else the exact-fp32 SIMT kernel.
- * precision: 0 = fp32 FMA (exact path), 1 = TF32 tensor cores, 2 = BF16 tensor cores (fp32 accumulate). */
+ * precision: 0 = fp32 FMA (exact path), 1 = TF32 tensor cores, 2 = BF16 (reserved: routed to the exact path),
+ *            3 = 3xTF32 split on tensor cores (fp32-class accuracy). */
 int ur_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
                 float* C, int64_t ldc, const float* bias /*nullable*/, int act, float* preact /*nullable*/, int64_t ldp,
                 int accumulate, int precision, void* stream);
@@ -75,11 +77,19 @@ int ur_gemm_simt_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, co
                      int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
                      void* stream);
 /* tcgen05 / TMEM / TMA kernel behind ur_gemm_f32 (csrc/gemm_tc.cu): TF32 operands read in place from fp32, fp32 accumulate.
- * Supports NT (A [M,K], B [N,K]) and TN (A stored [K,M], B stored [K,N], split-K with atomic accumulate) when N % 128 == 0 and
- * K % 32 == 0; returns UR_ERR_UNSUPPORTED otherwise. */
+ * Supports NT (A [M,K], B [N,K]), NN (B stored [K,N]) and TN (A stored [K,M], B stored [K,N], split-K with atomic accumulate)
+ * when N % 128 == 0 and K % 32 == 0; returns UR_ERR_UNSUPPORTED otherwise. */
 int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                    int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
                    int precision, void* stream);
+/* ur_gemm_f32 with two fused epilogue stages (csrc/gemm_tc.cu; unfused SIMT route otherwise):
+ *   dact   (nullable): C = (op(A) op(B)) * act'(dact[row, col])      -- replaces: autograd of the FFN activation, modules.py:348-351
+ *   colsum (nullable): colsum[col] += sum_rows C[row, col]           -- the bias gradient of the layer that consumes C as dy
+ * precision 3 = 3xTF32 split (hi/lo operand split in shared memory, fp32-class results from the tensor pipe). */
+int ur_gemm_fused_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                      int64_t ldb, float* C, int64_t ldc, const float* bias /*nullable*/, int act, float* preact /*nullable*/,
+                      int64_t ldp, int accumulate, int precision, const float* dact /*nullable*/, int64_t ldd,
+                      float* colsum /*nullable*/, void* stream);
 /* out[c][r] = in[r][c] for small weight matrices (dx = dy W is issued as an NT product on W^T) */
 int ur_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
 /* dY *= act'(preact) */

@@ -201,6 +201,22 @@ def test_trainer_fit_loop_and_checkpoint(tmp_path):
     assert set(model2.state_dict()) == set(model.state_dict())
 
 
+def test_sasrec_d128_3xtf32_tensor_core_path_meets_fp32_bar():
+    """gemm_precision=tf32x3 (the bench default): tcgen05 GEMMs with the hi/lo operand split -> the fp32 parity bar (1e-3) holds."""
+    g = Golden('sasrec_softmax_d128')
+    model, _ = cuda_model(g, table_update='dense', gemm_precision='tf32x3')
+    model.train()
+    loss, scores, user_emb, _ = model(**to_dev(g.fwd_batch()), return_loss_only=False)
+    assert abs(float(loss) - float(g.loss)) <= 1e-4 * abs(float(g.loss))
+    assert rel_err(scores.cpu(), g.scores) < 1e-4 and rel_err(user_emb.cpu(), g.user_emb) < 1e-4
+    loss.backward()
+    scale = max(float(v.abs().max()) for v in g.grads.values())
+    for k, p in model.named_parameters():
+        ref = g.grads[k]
+        err = float((p.grad.cpu().double() - ref.double()).abs().max())
+        assert err <= 1e-3 * max(float(ref.abs().max()), 1e-2 * scale), (k, err)
+
+
 def test_sasrec_d128_tf32_tensor_core_path():
     """gemm_precision=tf32 routes the encoder GEMMs through tcgen05; parity bar for reduced-precision modes is 1e-2."""
     g = Golden('sasrec_softmax_d128')

@@ -385,6 +385,82 @@ def test_gemm_tc_tn_weight_grad(Mo, No, T):
     assert rel(dW, ref) < TF32_TOL
 
 
+@pytest.mark.parametrize('M,N,K', [(300, 128, 128), (1000, 128, 512), (5000, 512, 128), (51200, 128, 384)])
+@pytest.mark.parametrize('precision', [1, 3])
+def test_gemm_tc_nn_input_grad(M, N, K, precision):
+    """dx[M,N] = dy[M,K] @ W[K,N]: A K-major, B MN-major (no transposed weight copy)."""
+    from unirec_b200 import ops
+    g = gen(24)
+    dY, W = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g) * 0.1
+    dX = torch.full((M, N), 3.0, device=DEV)
+    ops.gemm(dY.to(DEV), W.to(DEV), dX, M, N, K, precision=precision)
+    ref = dY.double() @ W.double()
+    assert rel(dX, ref) < (TF32_TOL if precision == 1 else X3_TOL)
+    ops.gemm(dY.to(DEV), W.to(DEV), dX, M, N, K, accumulate=True, precision=precision)
+    assert rel(dX, 2 * ref) < (TF32_TOL if precision == 1 else X3_TOL)
+
+
+X3_TOL = 1e-5       # 3xTF32 split: dropped terms are O(2^-22) per product -> fp32-class results
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 128, 128), (1000, 384, 128), (777, 512, 512), (51200, 128, 512)])
+@pytest.mark.parametrize('act', [None, 'swish'])
+def test_gemm_tc_3xtf32_nt(M, N, K, act):
+    """precision=3: hi/lo operand split in shared memory, three tcgen05 MMAs per k-step -> same bar as the exact fp32 path."""
+    from unirec_b200 import ops
+    g = gen(25)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.1, torch.randn(N, generator=g)
+    C, pre = torch.full((M, N), 7.0, device=DEV), torch.empty(M, N, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), C, M, N, K, transB=True, bias=b.to(DEV), act=act, preact=pre, precision=3)
+    ref_pre = O.linear(A.double(), W.double(), b.double())
+    ref = O.activation(ref_pre, act) if act else ref_pre
+    assert rel(pre, ref_pre) < X3_TOL and rel(C, ref) < X3_TOL
+    # not worse than the exact-FMA kernel against the float64 product
+    C0 = torch.empty(M, N, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), C0, M, N, K, transB=True, bias=b.to(DEV), precision=0)
+    assert rel(pre, ref_pre) < 8 * rel(C0, ref_pre) + 1e-6
+
+
+@pytest.mark.parametrize('Mo,No,T', [(128, 128, 5024), (384, 128, 51200), (128, 512, 4096)])
+def test_gemm_tc_3xtf32_tn_weight_grad(Mo, No, T):
+    from unirec_b200 import ops
+    g = gen(26)
+    dY, X = torch.randn(T, Mo, generator=g), torch.randn(T, No, generator=g)
+    dW = torch.zeros(Mo, No, device=DEV)
+    ops.gemm(dY.to(DEV), X.to(DEV), dW, Mo, No, T, transA=True, lda=Mo, accumulate=True, precision=3)
+    assert rel(dW, dY.double().t() @ X.double()) < X3_TOL
+
+
+@pytest.mark.parametrize('precision', [0, 1, 3])
+@pytest.mark.parametrize('M,N,K', [(640, 512, 128), (5000, 128, 128)])
+def test_gemm_fused_act_bwd_and_colsum(M, N, K, precision):
+    """dh = (dz @ W) * act'(hpre) with colsum(dh) accumulated: the FFN backward epilogue fusion (modules.py:348-351 autograd)."""
+    from unirec_b200 import ops
+    g = gen(27)
+    dZ, W, pre = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g) * 0.1, torch.randn(M, N, generator=g)
+    dH = torch.empty(M, N, device=DEV)
+    cs = torch.ones(N, device=DEV)
+    ops.gemm_fused(dZ.to(DEV), W.to(DEV), dH, M, N, K, precision=precision, dact=pre.to(DEV), act='swish', colsum=cs)
+    pre64 = pre.double().requires_grad_()
+    O.activation(pre64, 'swish').sum().backward()
+    ref = (dZ.double() @ W.double()) * pre64.grad
+    tol = {0: 1e-5, 1: TF32_TOL, 3: X3_TOL}[precision]
+    assert rel(dH, ref) < tol
+    assert rel(cs, 1.0 + ref.sum(0)) < 10 * tol
+
+
+def test_add_ln_bwd_fused_bias_grad():
+    from unirec_b200 import ops
+    g = gen(28)
+    T, d = 1000, 128
+    Z, dY, gamma = torch.randn(T, d, generator=g), torch.randn(T, d, generator=g), torch.rand(d, generator=g) + 0.5
+    mean = Z.mean(1)
+    rstd = 1.0 / torch.sqrt(Z.var(1, unbiased=False) + 1e-10)
+    dZ, dg, db, dzs = (torch.empty(T, d, device=DEV), torch.zeros(d, device=DEV), torch.zeros(d, device=DEV), torch.ones(d, device=DEV))
+    ops.add_ln_bwd(Z.to(DEV), gamma.to(DEV), mean.to(DEV), rstd.to(DEV), dY.to(DEV), dZ, dg, db, dzsum=dzs)
+    assert rel(dzs, 1.0 + dZ.double().sum(0).cpu()) < 1e-5
+
+
 def test_transpose_small():
     from unirec_b200 import ops
     w = torch.randn(384, 128, generator=gen(23))

@@ -21,10 +21,11 @@ SIGNATURES = {
     'ur_seq_prep_ln_fwd_f32': 'ppppfpliipppp',
     'ur_seq_prep_ln_bwd_f32': 'pppplii' + 'ppp' + 'pppp' + 'p',
     'ur_add_ln_fwd_f32': 'plplppflipl' + 'ppp',
-    'ur_add_ln_bwd_f32': 'plppp' + 'pl' + 'pl' + 'li' + 'pl' + 'ppp',
+    'ur_add_ln_bwd_f32': 'plppp' + 'pl' + 'pl' + 'li' + 'pl' + 'pppp',
     'ur_gemm_f32': 'iilllplplplpipliip',
     'ur_gemm_simt_f32': 'iilllplplplpiplip',
     'ur_gemm_tc_f32': 'iilllplplplpipliip',
+    'ur_gemm_fused_f32': 'iilllplplplpipliiplpp',
     'ur_transpose_f32': 'pllpp',
     'ur_act_bwd_f32': 'pplip',
     'ur_colsum_accum_f32': 'plllpp',

@@ -117,4 +117,14 @@ __device__ __forceinline__ float act_bwd(float x, int act) {
     }
 }
 
+// fast-intrinsic derivative for the reduced-precision (TF32) GEMM epilogue
+__device__ __forceinline__ float act_bwd_fast(float x, int act) {
+    switch (act) {
+        case ACT_SWISH: { float s = __fdividef(1.f, 1.f + __expf(-x)); return s * (1.f + x * (1.f - s)); }
+        case ACT_SIGMOID: { float s = __fdividef(1.f, 1.f + __expf(-x)); return s * (1.f - s); }
+        case ACT_RELU: return x > 0.f ? 1.f : 0.f;
+        default: return act_bwd(x, act);
+    }
+}
+
 }  // namespace ur

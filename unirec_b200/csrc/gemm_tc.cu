@@ -3,15 +3,17 @@
 //
 //   C[M, N] (+)= act(op(A) * op(B) + bias)
 //
-// Two operand layouts, selected by the caller's transposes:
-//   NT  (forward, y = x W^T)   : A [M,K] and B [N,K] both K-major          -> kTN = false
-//   TN  (weight grads, dW = dy^T x): A stored [K,M], B stored [K,N], both MN-major -> kTN = true
-// (NN, dx = dy W, is routed through NT with a transposed copy of the small weight matrix, see ur_transpose_f32.)
+// Operand layouts, selected by the caller's transposes (template flags kAmn / kBmn = operand is MN-major in memory):
+//   NT  (forward, y = x W^T)        : A [M,K] and B [N,K] both K-major
+//   NN  (input grads, dx = dy W)    : A [M,K] K-major, B stored [K,N] MN-major (no transposed weight copies)
+//   TN  (weight grads, dW = dy^T x) : A stored [K,M], B stored [K,N], both MN-major, split-K over the token dimension
 //
-// One CTA owns a 128-row stripe of C and up to 512 columns (the whole TMEM: 128 lanes x 512 fp32 columns), so the A stripe
-// is read from HBM once.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> bias/activation -> shared-memory transpose -> coalesced 128-byte row stores).
+// Persistent kernel, one CTA per SM looping over (row stripe, column chunk, k split) work units.  Warp roles: warp 0 = TMA
+// producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..9 = epilogue (tcgen05.ld -> bias / activation /
+// activation-backward / column sums -> swizzled shared-memory chunk -> TMA store or reduce-add), warps 10..13 = operand
+// splitter of the 3xTF32 mode.  Two TMEM accumulators: the epilogue of one unit overlaps the main loop of the next.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ur {
@@ -19,9 +21,7 @@ namespace tc {
 
 constexpr int BM = 128;          // rows of C per CTA (UMMA M)
 constexpr int BK = 32;           // fp32 elements per k-block = 128 bytes = one swizzle span
-constexpr int MAX_NC = 256;      // columns of C per CTA: 256 TMEM columns and <= 100 KB smem -> 2 CTAs per SM, so one CTA's
-                                 // epilogue overlaps the other's TMA/MMA main loop (the A stripe is re-read from L2 per chunk)
-constexpr int NUM_THREADS = 192;
+constexpr int MAX_NC = 256;      // columns of C per work unit: two accumulators of NC columns fill the 512 TMEM columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,164 +83,347 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 // instruction descriptor: D=f32, A=B=tf32, M=128, N=n; major bits: 0 = K-major, 1 = MN-major
-__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct Params {
     int M, N, K;            // logical GEMM sizes (K = reduction length)
-    int NC;                 // columns handled by one CTA (multiple of 128, <= 512)
+    int NC;                 // columns handled by one work unit (128 or 256)
     int stages;
     float* C; int64_t ldc;
     const float* bias; int act;
     float* preact; int64_t ldp;
+    const float* dact; int64_t ldd;   // optional: C = acc * act'(dact[row, col])  (fused activation backward)
+    float* colsum;                    // optional: colsum[col] += sum over rows of the stored C values (fused bias gradient)
     int accumulate;         // 0 store, 1 atomic add (split-K partials), 2 read-add-store
-    int tmem_cols;
-    int kb_per_split;       // k-blocks handled by one CTA along grid.z
+    int kb_per_split;       // k-blocks handled by one work unit along the split dimension
+    int epi_bufs;           // store buffers per epilogue warp (1 or 2)
+    int dbg_skip;           // bring-up: bit0 skip TMA store issue, bit1 skip bias, bit2 skip smem staging
+    int n_chunks, m_stripes, total_units;
     int dbg_lbo, dbg_sbo, dbg_kstep, dbg_major, dbg_layout;   // MN-major descriptor parameters (bytes / flags), tunable for bring-up
 };
 
 static int g_dbg_lbo = 32 * BK * 4, g_dbg_sbo = 512, g_dbg_kstep = 1024, g_dbg_major = 1, g_dbg_layout = 1, g_dbg_tma_swz = 4;
 
-template <bool kTN>
-__global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                 const __grid_constant__ CUtensorMap tmB, const Params p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float to_tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// Activation stages of the epilogue.  The common activations get tight unrolled loops; everything else goes through one
+// out-of-line call per element.  (Inlining the 5-way switch with erff/tanhf into a 32-element unrolled loop produced ~100 KB
+// of SASS per kernel and made the epilogue instruction-fetch bound: 140 us instead of 40 us for the FFN GEMMs.)
+__device__ __noinline__ float act_fwd_generic(float x, int act) { return act_fwd(x, act); }
+__device__ __noinline__ float act_bwd_generic(float x, int act) { return act_bwd(x, act); }
+
+template <bool kPrecise>
+__device__ __forceinline__ void epilogue_act_fwd(float (&v)[32], int act) {
+    if (act == ACT_SWISH) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = kPrecise ? v[i] / (1.f + expf(-v[i])) : __fdividef(v[i], 1.f + __expf(-v[i]));
+    } else if (act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = act_fwd_generic(v[i], act);
+    }
+}
+template <bool kPrecise>
+__device__ __forceinline__ float swish_bwd(float x) {
+    const float s = kPrecise ? 1.f / (1.f + expf(-x)) : __fdividef(1.f, 1.f + __expf(-x));
+    return s * (1.f + x * (1.f - s));
+}
+template <bool kPrecise>
+__device__ __forceinline__ void epilogue_act_bwd(float (&v)[32], const float4 (&z)[8], int act) {
+    if (act == ACT_SWISH) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[4 * i] *= swish_bwd<kPrecise>(z[i].x); v[4 * i + 1] *= swish_bwd<kPrecise>(z[i].y);
+            v[4 * i + 2] *= swish_bwd<kPrecise>(z[i].z); v[4 * i + 3] *= swish_bwd<kPrecise>(z[i].w);
+        }
+    } else if (act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[4 * i] = z[i].x > 0.f ? v[4 * i] : 0.f; v[4 * i + 1] = z[i].y > 0.f ? v[4 * i + 1] : 0.f;
+            v[4 * i + 2] = z[i].z > 0.f ? v[4 * i + 2] : 0.f; v[4 * i + 3] = z[i].w > 0.f ? v[4 * i + 3] : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[4 * i] *= act_bwd_generic(z[i].x, act); v[4 * i + 1] *= act_bwd_generic(z[i].y, act);
+            v[4 * i + 2] *= act_bwd_generic(z[i].z, act); v[4 * i + 3] *= act_bwd_generic(z[i].w, act);
+        }
+    }
+}
+
+constexpr int EPI_WARPS = 8;                  // two warps per TMEM lane block, interleaved over the 32-column chunks
+constexpr int EPI_TILE_FLOATS = 32 * 32;      // per epilogue warp and buffer: 32 rows x 32 columns, 128-byte swizzled (TMA store source)
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue,
+// warps 10..13 (kSplit only) = operand splitter.  Two TMEM accumulators (2 x NC columns): the epilogue of unit i overlaps the
+// main loop of unit i+1.
+//
+// kSplit ("3xTF32"): every staged fp32 tile x is rewritten in shared memory as hi = tf32(x) (in place) and lo = tf32(x - hi)
+// (second buffer, same swizzled layout -> the split is purely elementwise on the raw tile bytes), and each k-step issues
+// lo*hi + hi*lo + hi*hi into the fp32 accumulator: the dropped terms are O(2^-22), i.e. fp32-class results from the tensor pipe.
+template <bool kAmn, bool kBmn, bool kSplit>
+__global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                       const __grid_constant__ CUtensorMap tmB,
+                                                                       const __grid_constant__ CUtensorMap tmC,
+                                                                       const __grid_constant__ CUtensorMap tmP, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];       // no static shared memory in this kernel: the window starts 1024-aligned
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC = p.NC, S = p.stages;
     const uint32_t a_bytes = BM * BK * 4;                 // 16 KB
     const uint32_t b_bytes = (uint32_t)NC * BK * 4;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t raw_bytes = a_bytes + b_bytes;
+    const uint32_t stage_bytes = kSplit ? 2 * raw_bytes : raw_bytes;      // [A | B | A_lo | B_lo]
     uint8_t* tiles = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    float* epi_stage = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);      // [8 warps][epi_bufs][32 x 32] swizzled
+    float* colsum_sm = epi_stage + EPI_WARPS * p.epi_bufs * EPI_TILE_FLOATS;          // [N] when p.colsum
+    uint64_t* full = reinterpret_cast<uint64_t*>(colsum_sm + (p.colsum ? p.N : 0));
     uint64_t* empty = full + S;
-    uint64_t* tmem_full = empty + S;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * NC;      // column chunks of one A stripe are adjacent in launch order
+    uint64_t* ready = empty + S;                   // kSplit: split finished (MMA waits on this instead of `full`)
+    uint64_t* tmem_full = ready + S;               // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     const int KB_all = (p.K + BK - 1) / BK;
-    const int kb_begin = blockIdx.z * p.kb_per_split;
-    const int KB = min(KB_all - kb_begin, p.kb_per_split);     // k-blocks of this CTA (>= 1 by construction)
+    const uint32_t tmem_cols = 2 * NC;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tmem_full, 1);
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+        if (p.preact) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+        for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(ready + s, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (p.colsum)
+        for (int c = threadIdx.x; c < p.N; c += blockDim.x) colsum_sm[c] = 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    // work unit u -> (column chunk, row stripe, k split); chunks of one A stripe are adjacent so they share it through L2
+    auto decode = [&](int u, int& m0, int& n0, int& kb_begin, int& KB) {
+        const int chunk = u % p.n_chunks;
+        const int rest = u / p.n_chunks;
+        m0 = (rest % p.m_stripes) * BM;
+        n0 = chunk * NC;
+        kb_begin = (rest / p.m_stripes) * p.kb_per_split;
+        KB = min(KB_all - kb_begin, p.kb_per_split);
+    };
+
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % S;
-                if (kb >= S) mbar_wait(empty + s, ((kb / S) - 1) & 1);
-                uint8_t* sa = tiles + (size_t)s * stage_bytes;
-                uint8_t* sb = sa + a_bytes;
-                mbar_expect_tx(full + s, stage_bytes);
-                const int kg = (kb_begin + kb) * BK;                                     // global k offset
-                if (!kTN) {
-                    tma_load_2d(sa, &tmA, full + s, kg, m0);                            // box [32 k] x [128 rows]
-                    for (int nb = 0; nb < NC / 128; ++nb)
-                        tma_load_2d(sb + (size_t)nb * 128 * BK * 4, &tmB, full + s, kg, n0 + nb * 128);
-                } else {
-                    // MN-major: box [32 m] x [32 k-rows]; 4 boxes cover 128 m, NC/32 boxes cover the n columns
-                    for (int mb = 0; mb < BM / 32; ++mb)
-                        tma_load_2d(sa + (size_t)mb * 32 * BK * 4, &tmA, full + s, m0 + mb * 32, kg);
-                    for (int nb = 0; nb < NC / 32; ++nb)
-                        tma_load_2d(sb + (size_t)nb * 32 * BK * 4, &tmB, full + s, n0 + nb * 32, kg);
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                int m0, n0, kb_begin, KB;
+                decode(u, m0, n0, kb_begin, KB);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % S;
+                    if (it >= (uint32_t)S) mbar_wait(empty + s, ((it / S) - 1) & 1);
+                    uint8_t* sa = tiles + (size_t)s * stage_bytes;
+                    uint8_t* sb = sa + a_bytes;
+                    mbar_expect_tx(full + s, raw_bytes);
+                    const int kg = (kb_begin + kb) * BK;                                     // global k offset
+                    if (!kAmn) {
+                        tma_load_2d(sa, &tmA, full + s, kg, m0);                            // box [32 k] x [128 rows]
+                    } else {                                                                 // box [32 m] x [32 k-rows], 4 boxes
+                        for (int mb = 0; mb < BM / 32; ++mb)
+                            tma_load_2d(sa + (size_t)mb * 32 * BK * 4, &tmA, full + s, m0 + mb * 32, kg);
+                    }
+                    if (!kBmn) {
+                        for (int nb = 0; nb < NC / 128; ++nb)
+                            tma_load_2d(sb + (size_t)nb * 128 * BK * 4, &tmB, full + s, kg, n0 + nb * 128);
+                    } else {
+                        for (int nb = 0; nb < NC / 32; ++nb)
+                            tma_load_2d(sb + (size_t)nb * 32 * BK * 4, &tmB, full + s, n0 + nb * 32, kg);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % S;
-                mbar_wait(full + s, (kb / S) & 1);
+            uint32_t it = 0, lt = 0;
+            const uint32_t idesc = make_idesc(NC, kAmn ? p.dbg_major : 0, kBmn ? p.dbg_major : 0);
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++lt) {
+                int m0, n0, kb_begin, KB;
+                decode(u, m0, n0, kb_begin, KB);
+                const uint32_t ab = lt & 1;
+                mbar_wait(tmem_empty + ab, ((lt >> 1) & 1) ^ 1);       // passes immediately for the first use of each buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
+                const uint32_t tacc = tmem_base + ab * (uint32_t)NC;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % S;
+                    mbar_wait((kSplit ? ready : full) + s, (it / S) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
 #pragma unroll
-                for (int k8 = 0; k8 < BK / 8; ++k8) {
-                    for (int nc = 0; nc < NC; nc += 256) {
-                        const int n_part = (NC - nc) < 256 ? (NC - nc) : 256;
+                    for (int k8 = 0; k8 < BK / 8; ++k8) {
                         uint64_t da, db;
-                        if (!kTN) {
-                            da = make_desc(sa + k8 * 32, 16, 1024);
-                            db = make_desc(sb + (uint32_t)nc * BK * 4 + k8 * 32, 16, 1024);
+                        if (!kAmn) da = make_desc(sa + k8 * 32, 16, 1024);
+                        else da = make_desc(sa + k8 * p.dbg_kstep, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
+                        if (!kBmn) db = make_desc(sb + k8 * 32, 16, 1024);
+                        else db = make_desc(sb + k8 * p.dbg_kstep, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
+                        if (kSplit) {
+                            // descriptor address field is in 16-byte units: the lo tiles sit raw_bytes further
+                            const uint64_t lo_off = (uint64_t)(raw_bytes >> 4);
+                            umma_tf32(tacc, da + lo_off, db, idesc, (kb | k8) != 0);       // a_lo * b_hi
+                            umma_tf32(tacc, da, db + lo_off, idesc, 1);                    // a_hi * b_lo
+                            umma_tf32(tacc, da, db, idesc, 1);                             // a_hi * b_hi
                         } else {
-                            // one instruction consumes 8 k-rows = one 1024-byte atom per 32-wide MN chunk
-                            da = make_desc(sa + k8 * p.dbg_kstep, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
-                            db = make_desc(sb + (uint32_t)nc * BK * 4 + k8 * p.dbg_kstep, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
+                            umma_tf32(tacc, da, db, idesc, (kb | k8) != 0);
                         }
-                        umma_tf32(tmem_base + (uint32_t)nc, da, db, make_idesc(n_part, kTN ? p.dbg_major : 0), (kb | k8) != 0);
                     }
+                    umma_commit(empty + s);          // frees this smem stage once the MMAs above have read it
                 }
-                umma_commit(empty + s);          // frees this smem stage once the MMAs above have read it
+                umma_commit(tmem_full + ab);         // accumulator complete
             }
-            umma_commit(tmem_full);              // accumulator complete
         }
-    } else {
-        // ---------------- epilogue: warps 2..5, TMEM lane block = warp % 4 ----------------
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    } else if (warp < 2 + EPI_WARPS) {
+        // ---------------- epilogue: warps 2..9, TMEM lane block = warp % 4, two warps per block ----------------
+        // Each warp owns 32 rows: tcgen05.ld a 32x32 chunk (lane = row), bias / activation / act' in registers, write the chunk
+        // into its own 128B-swizzled 4 KB buffer and hand it to the TMA engine (store, or reduce-add for the accumulate modes):
+        // no global store instructions, no read-add-store round trip, two buffers per warp so the next chunk overlaps the copy.
         const int lb = warp & 3;                                   // lanes [32*lb, 32*lb+32)
-        float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * 36;   // pipeline smem is free now
-        const int row = m0 + lb * 32 + lane;
-        for (int c0 = 0; c0 < NC; c0 += 32) {
-            float v[32];
-            tmem_ld_x32(tmem_base + ((uint32_t)(lb * 32) << 16) + (uint32_t)c0, v);
-            const int ncol = n0 + c0;
-            if (p.bias && blockIdx.z == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + i));
-                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+        const int half = (warp - 2) >> 2;                          // which of the two warps of this lane block
+        const int nbuf = p.epi_bufs;
+        float* bufs = epi_stage + (size_t)(warp - 2) * nbuf * EPI_TILE_FLOATS;
+        uint32_t lt = 0, nstore = 0;
+        auto emit = [&](const CUtensorMap* map, const float* v, bool reduce, int col, int row0) -> const float* {
+            float* buf = bufs + (nbuf == 2 ? (nstore & 1) : 0) * EPI_TILE_FLOATS;
+            if (nstore >= (uint32_t)nbuf) {          // the copy engine must have finished reading this buffer
+                if (lane == 0) {
+                    if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
+                __syncwarp();
             }
-            for (int pass = 0; pass < 2; ++pass) {
-                float* out = pass == 0 ? p.preact : p.C;
-                const int64_t ld = pass == 0 ? p.ldp : p.ldc;
-                if (out == nullptr) continue;
-                if (pass == 1 && p.act != ACT_NONE) {
+            if (!(p.dbg_skip & 4)) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = act_fwd_fast(v[i], p.act);
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(buf + lane * 32 + ((i ^ (lane & 7)) << 2)) =
+                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0 && !(p.dbg_skip & 1)) {
+                if (reduce) tma_reduce_add_2d(map, buf, col, row0);
+                else tma_store_2d(map, buf, col, row0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++nstore;
+            return buf;
+        };
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++lt) {
+            int m0, n0, kb_begin, KB;
+            decode(u, m0, n0, kb_begin, KB);
+            const int row0 = m0 + lb * 32;
+            const int64_t grow = min(row0 + lane, p.M - 1);       // clamp: out-of-range rows are clipped by the TMA store
+            float4 dnext[8];
+            auto load_dact = [&](int col) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dnext[i] = __ldg(reinterpret_cast<const float4*>(p.dact + grow * p.ldd + col) + i);
+            };
+            if (p.dact) load_dact(n0 + half * 32);
+            const uint32_t ab = lt & 1;
+            mbar_wait(tmem_full + ab, (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + ab * (uint32_t)NC + ((uint32_t)(lb * 32) << 16);
+            for (int c0 = half * 32; c0 < NC; c0 += 64) {
+                float v[32];
+                tmem_ld_x32(tacc + (uint32_t)c0, v);
+                if (c0 + 64 >= NC) {          // this warp's last read of the accumulator: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty + ab);
                 }
-                __syncwarp();
+                const int ncol = n0 + c0;
+                if (p.bias && kb_begin == 0 && !(p.dbg_skip & 2)) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                __syncwarp();
-                // coalesced: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int r = it * 4 + (lane >> 3), c = (lane & 7) * 4;
-                    const int grow = m0 + lb * 32 + r;
-                    if (grow < p.M) {
-                        float4 x = *reinterpret_cast<const float4*>(stage + r * 36 + c);
-                        float* dst = out + (int64_t)grow * ld + ncol + c;
-                        if (pass == 1 && p.accumulate == 1) { red_add_v4(dst, x); continue; }
-                        if (pass == 1 && p.accumulate == 2) x = f4_add(x, *reinterpret_cast<const float4*>(dst));
-                        *reinterpret_cast<float4*>(dst) = x;
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + i));
+                        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                     }
+                }
+                if (p.preact) emit(&tmP, v, false, ncol, row0);
+                if (p.dact) {
+                    epilogue_act_bwd<kSplit>(v, dnext, p.act);
+                    if (c0 + 64 < NC) load_dact(ncol + 64);
+                } else if (p.act != ACT_NONE) {
+                    epilogue_act_fwd<kSplit>(v, p.act);
+                }
+                const float* buf = emit(&tmC, v, p.accumulate != 0, ncol, row0);
+                if (p.colsum) {
+                    // lane c sums column c of the staged chunk over this warp's (valid) rows: conflict-free transposed read
+                    const int nrows = min(32, p.M - row0);
+                    float cs = 0.f;
+                    for (int r = 0; r < nrows; ++r) cs += buf[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+                    atomicAdd(colsum_sm + ncol + lane, cs);
                 }
             }
         }
-        (void)row;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+    } else if (kSplit) {
+        // ---------------- splitter: warps 10..13 ----------------
+        const int tid = threadIdx.x - (2 + EPI_WARPS) * 32;
+        const int n4 = (int)(raw_bytes >> 4);
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            int m0, n0, kb_begin, KB;
+            decode(u, m0, n0, kb_begin, KB);
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % S;
+                mbar_wait(full + s, (it / S) & 1);
+                float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * stage_bytes);
+                float4* lo = reinterpret_cast<float4*>(tiles + (size_t)s * stage_bytes + raw_bytes);
+#pragma unroll 4
+                for (int i = tid; i < n4; i += 128) {
+                    const float4 x = hi[i];
+                    float4 h, l;
+                    h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
+                    l.x = to_tf32_rna(x.x - h.x); l.y = to_tf32_rna(x.y - h.y); l.z = to_tf32_rna(x.z - h.z); l.w = to_tf32_rna(x.w - h.w);
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready + s);
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (p.colsum)                                        // one atomic per column per CTA
+        for (int c = threadIdx.x; c < p.N; c += blockDim.x) atomicAdd(p.colsum + c, colsum_sm[c]);
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -302,64 +485,99 @@ int ur_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, vo
     UR_RETURN_LAST_ERROR();
 }
 
-// Returns UR_ERR_UNSUPPORTED when the shape/layout is outside the tensor-core kernel; the dispatcher then uses the SIMT kernel.
-int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
-                   float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate, int precision,
-                   void* stream) {
+// Extended tensor-core GEMM behind ur_gemm_f32 / ur_gemm_fused_f32.  precision: 1 = TF32 (operands truncated by the tensor
+// pipe), 3 = 3xTF32 split (fp32-class).  Returns UR_ERR_UNSUPPORTED when the shape/layout is outside the kernel; the dispatcher
+// then uses the SIMT kernel (plus separate act_bwd / colsum launches).
+int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                  float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate, int precision,
+                  const float* dact, int64_t ldd, float* colsum, void* stream) {
     using namespace ur::tc;
-    if (precision != 1) return UR_ERR_UNSUPPORTED;                       // TF32 only for now
-    const bool nt = !transA && transB, tn = transA && !transB;
-    if (!nt && !tn) return UR_ERR_UNSUPPORTED;
+    if (precision != 1 && precision != 3) return UR_ERR_UNSUPPORTED;
+    const bool split3 = precision == 3;
+    const bool a_mn = transA != 0;           // A stored [K, M]
+    const bool b_mn = transB == 0;           // B stored [K, N]
+    if (a_mn && !b_mn) return UR_ERR_UNSUPPORTED;                           // TT is never needed by the path
     if (M < 1 || N < 128 || (N % 128) || K < BK || (K % BK)) return UR_ERR_UNSUPPORTED;
-    if ((lda & 3) || (ldb & 3) || (ldc & 3) || (preact && (ldp & 3))) return UR_ERR_UNSUPPORTED;
+    if ((lda & 3) || (ldb & 3) || (ldc & 3) || (preact && (ldp & 3)) || (dact && (ldd & 3))) return UR_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) return UR_ERR_UNSUPPORTED;
-    if (tn && (M % 32)) return UR_ERR_UNSUPPORTED;
-    // columns per CTA: largest multiple of 128 that divides N and fits TMEM
+    if (a_mn && (M % 32)) return UR_ERR_UNSUPPORTED;
+    if (dact && (accumulate || preact)) return UR_ERR_UNSUPPORTED;
+    // columns per work unit: two accumulators must fit the 512 TMEM columns; the split kernel keeps hi+lo tiles -> 128
+    static const int env_max_nc = getenv("UR_TC_MAX_NC") ? atoi(getenv("UR_TC_MAX_NC")) : 0;         // tuning knobs (profiles/gemm_shapes.py)
+    static const int env_bufs = getenv("UR_TC_EPI_BUFS") ? atoi(getenv("UR_TC_EPI_BUFS")) : 0;
+    static const int env_stages = getenv("UR_TC_STAGES") ? atoi(getenv("UR_TC_STAGES")) : 0;
+    const int max_nc = split3 ? 128 : (env_max_nc ? env_max_nc : MAX_NC);
     int NC = 0;
-    for (int c = MAX_NC; c >= 128; c -= 128)
+    for (int c = max_nc; c >= 128; c -= 128)
         if (N % c == 0) { NC = c; break; }
     if (!NC) return UR_ERR_UNSUPPORTED;
-    const uint32_t stage_bytes = BM * BK * 4 + (uint32_t)NC * BK * 4;
-    int stages = (int)((100 * 1024) / stage_bytes);      // two CTAs per SM
+    const uint32_t raw_bytes = BM * BK * 4 + (uint32_t)NC * BK * 4;
+    const uint32_t stage_bytes = split3 ? 2 * raw_bytes : raw_bytes;
+    // one persistent CTA per SM: 3 x 64 KB (split) / 3 x 48 KB / 5 x 32 KB of operand stages + 32 or 64 KB of epilogue store buffers
+    const int epi_bufs = env_bufs ? env_bufs : (split3 ? 1 : 2);
+    int stages = (int)(((split3 ? 192 : 160) * 1024) / stage_bytes);
     const int KB = (int)(K / BK);
     // split-K along the reduction (token) dimension when the output has too few tiles to fill the GPU (weight gradients)
-    const int64_t tiles = ((M + BM - 1) / BM) * (N / NC);
+    const int64_t m_stripes = (M + BM - 1) / BM;
+    const int64_t tiles = m_stripes * (N / NC);
     int splits = 1;
-    if (accumulate && !preact && act == 0 && !bias && tiles < ur::kNumSMs) {
+    if (accumulate && !preact && act == 0 && !bias && !colsum && tiles < ur::kNumSMs) {
         splits = (int)((ur::kNumSMs + tiles - 1) / tiles);
-        if (splits > KB / 8) splits = KB / 8 > 0 ? KB / 8 : 1;          // at least 8 k-blocks per CTA
+        if (splits > KB / 8) splits = KB / 8 > 0 ? KB / 8 : 1;          // at least 8 k-blocks per unit
     }
     int kb_per_split = (KB + splits - 1) / splits;
     splits = (KB + kb_per_split - 1) / kb_per_split;
-    if (stages > 4) stages = 4;
-    if (stages > kb_per_split) stages = kb_per_split;
-    if (stages < 1) return UR_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
-    CUtensorMap tmA, tmB;
+    if (stages > 6) stages = 6;
+    if (env_stages && stages > env_stages) stages = env_stages;
+    if (stages < 2) return UR_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)EPI_WARPS * epi_bufs * EPI_TILE_FLOATS * sizeof(float) + (colsum ? (size_t)N * 4 : 0) +
+                        (3 * stages + 4) * sizeof(uint64_t) + 16;
+    if (smem > 227 * 1024) return UR_ERR_UNSUPPORTED;
+    CUtensorMap tmA, tmB, tmC, tmP;
     bool ok;
-    if (nt) {   // A [M,K] (ld lda), B [N,K] (ld ldb): inner = k
-        ok = make_map(&tmA, A, M, K, lda, BK, BM) && make_map(&tmB, B, N, K, ldb, BK, 128);
-    } else {    // A stored [K,M] (ld lda), B stored [K,N] (ld ldb): inner = m / n, rows = k
-        const CUtensorMapSwizzle swz = (CUtensorMapSwizzle)g_dbg_tma_swz;      // 4 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-        ok = make_map(&tmA, A, K, M, lda, 32, BK, swz) && make_map(&tmB, B, K, N, ldb, 32, BK, swz);
-    }
+    const CUtensorMapSwizzle swz_mn = (CUtensorMapSwizzle)g_dbg_tma_swz;      // 4 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+    if (!a_mn) ok = make_map(&tmA, A, M, K, lda, BK, BM);                      // A [M,K]: inner = k
+    else ok = make_map(&tmA, A, K, M, lda, 32, BK, swz_mn);                    // A stored [K,M]: inner = m, rows = k
+    if (!b_mn) ok = ok && make_map(&tmB, B, N, K, ldb, BK, 128);               // B [N,K]
+    else ok = ok && make_map(&tmB, B, K, N, ldb, 32, BK, swz_mn);              // B stored [K,N]
+    ok = ok && make_map(&tmC, C, M, N, ldc, 32, 32);                           // epilogue store boxes: 32 columns x 32 rows
+    tmP = tmC;
+    if (preact) ok = ok && make_map(&tmP, preact, M, N, ldp, 32, 32);
     if (!ok) return UR_ERR_UNSUPPORTED;
     Params p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.NC = NC; p.stages = stages; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act;
-    p.preact = preact; p.ldp = ldp; p.accumulate = accumulate ? (splits > 1 ? 1 : 2) : 0;
-    p.tmem_cols = NC <= 128 ? 128 : (NC <= 256 ? 256 : 512);
-    p.kb_per_split = kb_per_split;
+    p.preact = preact; p.ldp = ldp; p.dact = dact; p.ldd = ldd; p.colsum = colsum;
+    p.accumulate = accumulate ? (splits > 1 ? 1 : 2) : 0;
+    p.kb_per_split = kb_per_split; p.epi_bufs = epi_bufs;
+    static const int env_skip = getenv("UR_TC_SKIP") ? atoi(getenv("UR_TC_SKIP")) : 0;
+    p.dbg_skip = env_skip;
+    p.n_chunks = (int)(N / NC); p.m_stripes = (int)m_stripes; p.total_units = (int)(tiles * splits);
     p.dbg_lbo = g_dbg_lbo; p.dbg_sbo = g_dbg_sbo; p.dbg_kstep = g_dbg_kstep; p.dbg_major = g_dbg_major; p.dbg_layout = g_dbg_layout;
-    dim3 grid((unsigned)(N / NC), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
+    const unsigned grid = (unsigned)(p.total_units < ur::kNumSMs ? p.total_units : ur::kNumSMs);
     cudaStream_t st = (cudaStream_t)stream;
-    if (nt) {
-        cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        gemm_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
+#define UR_TC_LAUNCH(AMN, BMN, SPL)                                                                                         \
+    do {                                                                                                                    \
+        cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        gemm_tc_kernel<AMN, BMN, SPL><<<grid, SPL ? 448 : 320, smem, st>>>(tmA, tmB, tmC, tmP, p);                                    \
+    } while (0)
+    if (split3) {
+        if (a_mn) UR_TC_LAUNCH(true, true, true);
+        else if (b_mn) UR_TC_LAUNCH(false, true, true);
+        else UR_TC_LAUNCH(false, false, true);
     } else {
-        cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        gemm_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
+        if (a_mn) UR_TC_LAUNCH(true, true, false);
+        else if (b_mn) UR_TC_LAUNCH(false, true, false);
+        else UR_TC_LAUNCH(false, false, false);
     }
+#undef UR_TC_LAUNCH
     UR_RETURN_LAST_ERROR();
+}
+
+int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                   float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate, int precision,
+                   void* stream) {
+    return ur_gemm_tc_ex(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, accumulate, precision, nullptr, 0,
+                         nullptr, stream);
 }
 
 }  // extern "C"

@@ -218,13 +218,14 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                          const float* dY, int64_t lddy, const float* __restrict__ dExtra, int64_t ldde,
                                                          int64_t rows, int d4, float* dZ, int64_t lddz,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         float* __restrict__ dzsum) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    RowRegs<MAXV> dgam, dbet;
-    zero_regs(dgam); zero_regs(dbet);
+    RowRegs<MAXV> dgam, dbet, dzs;
+    zero_regs(dgam); zero_regs(dbet); zero_regs(dzs);
     for (int64_t r = warp0; r < rows; r += nwarps) {
         const float4* zr = reinterpret_cast<const float4*>(Z + r * ldz);
         const float4* dyr = reinterpret_cast<const float4*>(dY + r * lddy);
@@ -244,11 +245,12 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             int c = lane + 32 * i;
-            if (c < d4) dzr[c] = dx.v[i];
+            if (c < d4) { dzr[c] = dx.v[i]; dzs.v[i] = f4_add(dzs.v[i], dx.v[i]); }
         }
     }
     block_accumulate<MAXV>(dgam, d4, dgamma, smem);
     block_accumulate<MAXV>(dbet, d4, dbeta, smem);
+    if (dzsum) block_accumulate<MAXV>(dzs, d4, dzsum, smem);     // bias gradient of the linear layer that produced Z
 }
 
 static inline int ln_grid(int64_t rows) {
@@ -320,7 +322,7 @@ int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R, int64_t ldr, const 
 
 int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const float* mean, const float* rstd, const float* dY,
                       int64_t lddy, const float* dExtra, int64_t ldde, int64_t rows, int d, float* dZ, int64_t lddz,
-                      float* dgamma, float* dbeta, void* stream) {
+                      float* dgamma, float* dbeta, float* dzsum, void* stream) {
     if (d <= 0 || (d & 3) || (ldz & 3) || (lddy & 3) || (ldde & 3) || (lddz & 3)) return UR_ERR_BAD_ARG;
     if (rows == 0) return UR_OK;
     const int d4 = d / 4;
@@ -329,7 +331,7 @@ int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const flo
     if (grid > ur::kNumSMs * 2) grid = ur::kNumSMs * 2;   // fewer CTAs -> fewer column atomics
 #define CALL(MV)                                                                                                    \
     ur::add_ln_bwd_kernel<MV><<<grid, 256, d * sizeof(float), st>>>(Z, ldz, (const float4*)gamma, mean, rstd, dY, lddy, \
-                                                                    dExtra, ldde, rows, d4, dZ, lddz, dgamma, dbeta);
+                                                                    dExtra, ldde, rows, d4, dZ, lddz, dgamma, dbeta, dzsum);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();

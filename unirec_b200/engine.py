@@ -17,7 +17,8 @@ import torch
 
 from . import ops
 
-PRECISION_CODES = {'fp32': 0, 'tf32': 1, 'bf16': 2}
+# 'fp32' = exact FMA (SIMT); 'tf32x3' = 3xTF32 split on tcgen05 (fp32-class accuracy); 'tf32' = single-pass TF32 tensor cores
+PRECISION_CODES = {'fp32': 0, 'tf32': 1, 'bf16': 2, 'tf32x3': 3}
 
 
 class Workspace:
@@ -136,18 +137,15 @@ def _lin_fwd(x, M, K, w, b, N, out, act=None, preact=None, lda=None, prec=0):
     return ops.gemm(x, w, out, M, N, K, transB=True, lda=lda, bias=b, act=act, preact=preact, precision=prec)
 
 
-_WT_WS = None      # workspace holding transposed weight copies for the tensor-core dx path (set by Engine.ensure_ready)
-
-
-def _lin_bwd(dy, M, N, x, K, w, dx, dw, db, lda_x=None, accumulate_dx=False, prec=0, lddy=None, lddx=None):
-    """y = x w^T + b.  dx[M,K] (+)= dy[M,N] @ w[N,K];  dw[N,K] += dy^T x;  db[N] += colsum(dy)."""
-    wt_ws = _WT_WS
+def _lin_bwd(dy, M, N, x, K, w, dx, dw, db, lda_x=None, accumulate_dx=False, prec=0, lddy=None, lddx=None, dact=None,
+             act=None, dx_colsum=None):
+    """y = x w^T + b.  dx[M,K] (+)= dy[M,N] @ w[N,K];  dw[N,K] += dy^T x;  db[N] += colsum(dy) (skipped when db is None:
+    the producer of dy already accumulated it).  dact/act: dx is multiplied by act'(dact) in the GEMM epilogue, and
+    dx_colsum receives the column sums of the result (bias gradient of the layer below)."""
     if dx is not None:
-        if prec != 0 and wt_ws is not None and K % 128 == 0 and N % 32 == 0:
-            # tensor-core path: dx = dy @ w is issued as an NT product on W^T (both operands K-major for tcgen05)
-            wt = wt_ws.get('wT_%dx%d' % (K, N), (K, N))
-            ops.transpose(w.view(N, K), wt)
-            ops.gemm(dy, wt, dx, M, K, N, transB=True, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec)
+        if dact is not None or dx_colsum is not None:
+            ops.gemm_fused(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec, dact=dact, act=act,
+                           colsum=dx_colsum)
         else:
             ops.gemm(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec)
     ops.gemm(dy, x, dw, N, K, M, transA=True, lda=lddy or N, ldb=lda_x, accumulate=True, precision=prec)
@@ -245,22 +243,22 @@ class SASRecTower:
             x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2 = self.saved[i]
             # x2 = LN(z2), z2 = ffn(x1) + x1
             dz2 = ws.get('dz2', (T, d))
+            # bias gradients ride on the kernels that produce the corresponding dy (no separate column-sum launches)
             ops.add_ln_bwd(z2, fp.p(f + 'LayerNorm.weight'), m2, r2, dx, dz2, fp.g(f + 'LayerNorm.weight'),
-                           fp.g(f + 'LayerNorm.bias'))
+                           fp.g(f + 'LayerNorm.bias'), dzsum=fp.g(f + 'dense_2.bias'))
             dh = ws.get('dh', (T, I))
-            _lin_bwd(dz2, T, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'),
-                     fp.g(f + 'dense_2.bias'), prec=prec)
-            ops.act_bwd(dh, hpre, self.act)
+            # dh = (dz2 @ W2) * act'(hpre), db1 += colsum(dh): one GEMM with a fused epilogue
+            _lin_bwd(dz2, T, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'), None, prec=prec,
+                     dact=hpre, act=self.act, dx_colsum=fp.g(f + 'dense_1.bias'))
             # dx1 = dz2 (residual) + dh @ W1   -> accumulate into dz2
-            _lin_bwd(dh, T, I, x1, d, fp.p(f + 'dense_1.weight'), dz2, fp.g(f + 'dense_1.weight'),
-                     fp.g(f + 'dense_1.bias'), accumulate_dx=True, prec=prec)
+            _lin_bwd(dh, T, I, x1, d, fp.p(f + 'dense_1.weight'), dz2, fp.g(f + 'dense_1.weight'), None,
+                     accumulate_dx=True, prec=prec)
             # x1 = LN(z1), z1 = attn_out + x
             dz1 = ws.get('dz1_%d' % (i % 2), (T, d))     # becomes this layer's input gradient (no copy)
             ops.add_ln_bwd(z1, fp.p(a + 'LayerNorm.weight'), m1, r1, dz2, dz1, fp.g(a + 'LayerNorm.weight'),
-                           fp.g(a + 'LayerNorm.bias'))
+                           fp.g(a + 'LayerNorm.bias'), dzsum=fp.g(a + 'dense.bias'))
             dctx = ws.get('dctx', (T, d))
-            _lin_bwd(dz1, T, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), fp.g(a + 'dense.bias'),
-                     prec=prec)
+            _lin_bwd(dz1, T, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec)
             dqkv = ws.get('dqkv', (T, 3 * d))
             ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv)
             wqkv, gwqkv = fp.span(a + 'query.weight', a + 'value.weight')
@@ -451,8 +449,6 @@ class Engine:
             if not p.data.is_contiguous():
                 p.data = p.data.contiguous()
         self.ws = Workspace(dev)
-        global _WT_WS
-        _WT_WS = self.ws
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._rowgrads = {}
 

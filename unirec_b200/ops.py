@@ -125,11 +125,11 @@ def add_ln_fwd(X, R, gamma, beta, eps, Y, mean, rstd, rows=None, d=None, ldx=Non
 
 
 def add_ln_bwd(Z, gamma, mean, rstd, dY, dZ, dgamma, dbeta, dExtra=None, rows=None, d=None, ldz=None, lddy=None,
-               ldde=None, lddz=None):
+               ldde=None, lddz=None, dzsum=None):
     d = d or Z.shape[-1]
     rows = rows if rows is not None else Z.numel() // d
     _call('ur_add_ln_bwd_f32', _f32(Z), ldz or d, _f32(gamma), _f32(mean), _f32(rstd), _f32(dY), lddy or d,
-          _f32(dExtra), ldde or d, rows, d, _f32(dZ), lddz or d, _f32(dgamma), _f32(dbeta), _stream())
+          _f32(dExtra), ldde or d, rows, d, _f32(dZ), lddz or d, _f32(dgamma), _f32(dbeta), _f32(dzsum), _stream())
     return dZ
 
 
@@ -145,6 +145,20 @@ def gemm(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None, ldc=N
         ldc = N
     _call('ur_gemm_f32', int(transA), int(transB), M, N, K, _f32(A), lda, _f32(B), ldb, _f32(C), ldc, _f32(bias),
           ACT_CODES[act], _f32(preact), ldp or N, int(accumulate), int(precision), _stream())
+    return C
+
+
+def gemm_fused(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, act=None,
+               preact=None, ldp=None, accumulate=False, precision=0, dact=None, ldd=None, colsum=None):
+    """gemm() plus two fused epilogue stages: C = (A @ B) * act'(dact) (activation backward) and colsum += column sums of C."""
+    if lda is None:
+        lda = M if transA else K
+    if ldb is None:
+        ldb = K if transB else N
+    if ldc is None:
+        ldc = N
+    _call('ur_gemm_fused_f32', int(transA), int(transB), M, N, K, _f32(A), lda, _f32(B), ldb, _f32(C), ldc, _f32(bias),
+          ACT_CODES[act], _f32(preact), ldp or N, int(accumulate), int(precision), _f32(dact), ldd or N, _f32(colsum), _stream())
     return C
 
 
