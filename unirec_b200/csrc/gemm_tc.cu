@@ -100,6 +100,7 @@ struct Params {
     int accumulate;         // 0 store, 1 atomic add (split-K partials), 2 read-add-store
     int kb_per_split;       // k-blocks handled by one work unit along the split dimension
     int epi_bufs;           // store buffers per epilogue warp (1 or 2)
+    int lo_stages;          // 3xTF32: depth of the lo ring
     int dbg_skip;           // bring-up: bit0 skip TMA store issue, bit1 skip bias, bit2 skip smem staging
     int n_chunks, m_stripes, total_units;
     int dbg_lbo, dbg_sbo, dbg_kstep, dbg_major, dbg_layout;   // MN-major descriptor parameters (bytes / flags), tunable for bring-up
@@ -110,10 +111,9 @@ static int g_dbg_lbo = 32 * BK * 4, g_dbg_sbo = 512, g_dbg_kstep = 1024, g_dbg_m
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// round-to-nearest (ties away) to the 10-bit TF32 mantissa with two full-rate integer ops (same result as cvt.rna.tf32.f32)
 __device__ __forceinline__ float to_tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // Activation stages of the epilogue.  The common activations get tight unrolled loops; everything else goes through one
@@ -194,14 +194,18 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
     const uint32_t a_bytes = BM * BK * 4;                 // 16 KB
     const uint32_t b_bytes = (uint32_t)NC * BK * 4;
     const uint32_t raw_bytes = a_bytes + b_bytes;
-    const uint32_t stage_bytes = kSplit ? 2 * raw_bytes : raw_bytes;      // [A | B | A_lo | B_lo]
+    const uint32_t stage_bytes = raw_bytes;               // raw ring: S stages of [A | B]
+    const int SL = kSplit ? p.lo_stages : 1;              // lo ring (3xTF32): SL stages of [A_lo | B_lo], SL <= S: the TMA prefetch
+                                                          // runs S deep (HBM latency), the split only SL deep (just ahead of the MMA)
     uint8_t* tiles = smem;
-    float* epi_stage = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);      // [8 warps][epi_bufs][32 x 32] swizzled
+    uint8_t* lo_tiles = smem + (size_t)S * stage_bytes;
+    float* epi_stage = reinterpret_cast<float*>(lo_tiles + (kSplit ? (size_t)SL * raw_bytes : 0));   // [8 warps][epi_bufs][32 x 32] swizzled
     float* colsum_sm = epi_stage + EPI_WARPS * p.epi_bufs * EPI_TILE_FLOATS;          // [N] when p.colsum
     uint64_t* full = reinterpret_cast<uint64_t*>(colsum_sm + (p.colsum ? p.N : 0));
     uint64_t* empty = full + S;
     uint64_t* ready = empty + S;                   // kSplit: split finished (MMA waits on this instead of `full`)
-    uint64_t* tmem_full = ready + S;               // [2]
+    uint64_t* lo_empty = ready + S;                // [SL] kSplit: the MMAs that read lo stage j have completed
+    uint64_t* tmem_full = lo_empty + SL;           // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     const int KB_all = (p.K + BK - 1) / BK;
@@ -213,6 +217,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
         if (p.preact) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
         for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(ready + s, 4); }
+        for (int s = 0; s < SL; ++s) mbar_init(lo_empty + s, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -290,17 +295,19 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                         else da = make_desc(sa + k8 * p.dbg_kstep, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
                         if (!kBmn) db = make_desc(sb + k8 * 32, 16, 1024);
                         else db = make_desc(sb + k8 * p.dbg_kstep, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
-                        if (kSplit) {
-                            // descriptor address field is in 16-byte units: the lo tiles sit raw_bytes further
-                            const uint64_t lo_off = (uint64_t)(raw_bytes >> 4);
-                            umma_tf32(tacc, da + lo_off, db, idesc, (kb | k8) != 0);       // a_lo * b_hi
-                            umma_tf32(tacc, da, db + lo_off, idesc, 1);                    // a_hi * b_lo
+                        if (kSplit && !(p.dbg_skip & 16)) {
+                            // same layout in the lo ring: only the start-address field (16-byte units) of the descriptors moves
+                            const uint32_t la = smem_u32(lo_tiles + (size_t)(it % SL) * raw_bytes);
+                            const uint64_t lo_off = (uint64_t)(((la - sa) & 0x3FFFFu) >> 4);
+                            umma_tf32(tacc, (da & ~0x3FFFull) | (((da & 0x3FFFull) + lo_off) & 0x3FFFull), db, idesc, (kb | k8) != 0);   // a_lo * b_hi
+                            umma_tf32(tacc, da, (db & ~0x3FFFull) | (((db & 0x3FFFull) + lo_off) & 0x3FFFull), idesc, 1);              // a_hi * b_lo
                             umma_tf32(tacc, da, db, idesc, 1);                             // a_hi * b_hi
                         } else {
                             umma_tf32(tacc, da, db, idesc, (kb | k8) != 0);
                         }
                     }
                     umma_commit(empty + s);          // frees this smem stage once the MMAs above have read it
+                    if (kSplit) umma_commit(lo_empty + (it % SL));
                 }
                 umma_commit(tmem_full + ab);         // accumulator complete
             }
@@ -401,8 +408,11 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int s = it % S;
                 mbar_wait(full + s, (it / S) & 1);
+                const int sl = it % SL;
+                if (it >= (uint32_t)SL) mbar_wait(lo_empty + sl, ((it / SL) - 1) & 1);
                 float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * stage_bytes);
-                float4* lo = reinterpret_cast<float4*>(tiles + (size_t)s * stage_bytes + raw_bytes);
+                float4* lo = reinterpret_cast<float4*>(lo_tiles + (size_t)sl * raw_bytes);
+                if (!(p.dbg_skip & 8))
 #pragma unroll 4
                 for (int i = tid; i < n4; i += 128) {
                     const float4 x = hi[i];
@@ -512,10 +522,12 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
         if (N % c == 0) { NC = c; break; }
     if (!NC) return UR_ERR_UNSUPPORTED;
     const uint32_t raw_bytes = BM * BK * 4 + (uint32_t)NC * BK * 4;
-    const uint32_t stage_bytes = split3 ? 2 * raw_bytes : raw_bytes;
+    const uint32_t stage_bytes = raw_bytes;
     // one persistent CTA per SM: 3 x 64 KB (split) / 3 x 48 KB / 5 x 32 KB of operand stages + 32 or 64 KB of epilogue store buffers
     const int epi_bufs = env_bufs ? env_bufs : (split3 ? 1 : 2);
-    int stages = (int)(((split3 ? 192 : 160) * 1024) / stage_bytes);
+    static const int env_lo = getenv("UR_TC_LO_STAGES") ? atoi(getenv("UR_TC_LO_STAGES")) : 0;
+    const int lo_stages = split3 ? (env_lo ? env_lo : 2) : 0;
+    int stages = (int)(((split3 ? 192 : 160) * 1024) / stage_bytes) - lo_stages;
     const int KB = (int)(K / BK);
     // split-K along the reduction (token) dimension when the output has too few tiles to fill the GPU (weight gradients)
     const int64_t m_stripes = (M + BM - 1) / BM;
@@ -530,8 +542,9 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     if (stages > 6) stages = 6;
     if (env_stages && stages > env_stages) stages = env_stages;
     if (stages < 2) return UR_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)stages * stage_bytes + (size_t)EPI_WARPS * epi_bufs * EPI_TILE_FLOATS * sizeof(float) + (colsum ? (size_t)N * 4 : 0) +
-                        (3 * stages + 4) * sizeof(uint64_t) + 16;
+    if (split3 && lo_stages > stages) return UR_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)(stages + lo_stages) * stage_bytes + (size_t)EPI_WARPS * epi_bufs * EPI_TILE_FLOATS * sizeof(float) + (colsum ? (size_t)N * 4 : 0) +
+                        (3 * stages + lo_stages + 5) * sizeof(uint64_t) + 16;
     if (smem > 227 * 1024) return UR_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmB, tmC, tmP;
     bool ok;
@@ -548,7 +561,7 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.NC = NC; p.stages = stages; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act;
     p.preact = preact; p.ldp = ldp; p.dact = dact; p.ldd = ldd; p.colsum = colsum;
     p.accumulate = accumulate ? (splits > 1 ? 1 : 2) : 0;
-    p.kb_per_split = kb_per_split; p.epi_bufs = epi_bufs;
+    p.kb_per_split = kb_per_split; p.epi_bufs = epi_bufs; p.lo_stages = lo_stages;
     static const int env_skip = getenv("UR_TC_SKIP") ? atoi(getenv("UR_TC_SKIP")) : 0;
     p.dbg_skip = env_skip;
     p.n_chunks = (int)(N / NC); p.m_stripes = (int)m_stripes; p.total_units = (int)(tiles * splits);
