@@ -127,7 +127,10 @@ int ur_loss_finish_f32(const float* loss_vec, int64_t B, const float* denom_dev 
 
 /* ---- K11+K12+K13: row-sparse gradient reduce fused with the optimizer (see csrc/sparse_opt.cu).
  * replaces: dense embedding grads + optim.Adam over whole tables + clip_grad_norm_, unirec/facility/trainer.py:134-152,346-349
- * head[V] must hold -1 between steps (apply restores it); n_uniq must be zeroed by the caller before the first link of a step. */
+ * head[V] must hold -1 between steps (apply restores it); n_uniq must be zeroed by the caller before the first link of a step.
+ * u_begin_dev / u_end_dev: device-resident bounds of the slice of the unique-row list to update (default: all of it); rows are
+ * appended in link order, so linking the history keys first makes [n_hist, n_uniq) the rows only the scorer touches -- those are
+ * updated on a side stream while the encoder backward runs (small_ctas = 1: CTAs sized to co-reside with a GEMM CTA). */
 int ur_rowlist_link(int32_t* head, const void* keys, int idx_bits, int64_t n, int64_t entry_offset, int32_t* next, int32_t* uniq,
                     int32_t* n_uniq, int64_t pad_id, void* stream);
 int ur_rowlist_apply_f32(float* table, float* mom, float* var, int d, int32_t* head, const int32_t* next, const int32_t* uniq,
@@ -135,6 +138,7 @@ int ur_rowlist_apply_f32(float* table, float* mom, float* var, int d, int32_t* h
                          int64_t coef0_group, int64_t n0, const float* src1, int64_t src1_group, const float* coef1,
                          int64_t coef1_group, int mode, float lr, float beta1, float beta2, float eps, float weight_decay,
                          const int32_t* step_dev, const float* grad_scale_dev, const int32_t* skip_flag, float* sqnorm_out,
+                         const int32_t* u_begin_dev /*nullable*/, const int32_t* u_end_dev /*nullable*/, int small_ctas,
                          void* stream);
 int ur_dense_opt_f32(float* param, const float* grad, float* mom, float* var, int64_t n, int mode, float lr, float beta1,
                      float beta2, float eps, float weight_decay, const int32_t* step_dev, const float* grad_scale_dev,

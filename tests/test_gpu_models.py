@@ -233,3 +233,89 @@ def test_sasrec_d128_tf32_tensor_core_path():
         ref = g.grads[k]
         err = float((p.grad.cpu().double() - ref.double()).abs().max())
         assert err <= 1e-2 * max(float(ref.abs().max()), 1e-2 * scale), (k, err)
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('name', ['sasrec_softmax', 'gru_bpr', 'sasrec_softmax_d128'])
+def test_trainer_overlapped_table_update_matches_serial(name, mode, tmp_path):
+    """Trainer.train_step with the early-linked, two-phase table update (target-only rows updated on a side stream during
+    the encoder backward) must land on the same parameters and optimizer state as the serial update."""
+    from unirec_b200.facility.accelerator import Accelerator
+    from unirec_b200.facility.trainer import Trainer
+    from unirec_b200.utils import argument_parser, general
+    g = Golden(name)
+    results = []
+    for overlap in (mode, 0):
+        args = dict(g.cfg)
+        args.update(exp_name='ovl', dataset='example', output_path=str(tmp_path), scheduler='none', optimizer='adam',
+                    learning_rate=1e-2, overlap_table_update=overlap, epochs=1)
+        cfg = argument_parser.parse_arguments(args, argv=[])
+        acc = Accelerator()
+        cfg['device'] = acc.device
+        general.init_seed(3)
+        model = general.get_class_instance(g.model, 'unirec_b200/model')(cfg).to(acc.device)
+        model.load_state_dict(g.params)
+        tr = Trainer(cfg, model, acc)
+        assert (model._engine.overlap_hook is not None) == bool(overlap)
+        losses = []
+        for step in range(4):
+            batch = to_dev(g.fwd_batch())
+            if step % 2:        # vary the batch: shift the ids (kept in range) so the row sets change between steps
+                V = int(g.cfg['n_items'])
+                batch['item_id'] = (batch['item_id'] % (V - 1)) + 1
+            losses.append(float(tr.train_step(batch)))
+        torch.cuda.synchronize()
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        opt_sd = tr.optimizer.state_dict()
+        results.append((losses, sd, opt_sd))
+    (l1, s1, o1), (l0, s0, o0) = results
+    assert max(abs(a - b) for a, b in zip(l1, l0)) < 1e-5 * max(abs(x) for x in l0)
+    for k in s0:
+        if k.endswith('key.bias'):       # mathematically zero gradient (softmax shift invariance): Adam amplifies its round-off
+            continue
+        assert rel_err(s1[k], s0[k]) < 1e-4, (k, rel_err(s1[k], s0[k]))
+    for tname in o0['tables']:
+        for mv in o0['tables'][tname]:
+            assert rel_err(o1['tables'][tname][mv].cpu(), o0['tables'][tname][mv].cpu()) < 1e-4, (tname, mv)
+    assert int(o1['step']) == int(o0['step']) == 4
+
+
+@pytest.mark.parametrize('name', ['sasrec_softmax', 'gru_bpr', 'mf_bpr', 'sasrec_softmax_d128'])
+def test_trainer_cuda_graph_step_matches_eager(name, tmp_path):
+    """Trainer.train_step replays the captured CUDA graph from the third step of a batch signature on: losses, parameters and
+    optimizer state must match the eager steps (same kernels, same order; atomics make runs agree to round-off, not bitwise)."""
+    from unirec_b200.facility.accelerator import Accelerator
+    from unirec_b200.facility.trainer import Trainer
+    from unirec_b200.utils import argument_parser, general
+    g = Golden(name)
+    results = []
+    for use_graph in (1, 0):
+        args = dict(g.cfg)
+        args.update(exp_name='cg', dataset='example', output_path=str(tmp_path), scheduler='none', optimizer='adam',
+                    learning_rate=1e-2, cuda_graph=use_graph, epochs=1)
+        cfg = argument_parser.parse_arguments(args, argv=[])
+        acc = Accelerator()
+        cfg['device'] = acc.device
+        general.init_seed(3)
+        model = general.get_class_instance(g.model, 'unirec_b200/model')(cfg).to(acc.device)
+        model.load_state_dict(g.params)
+        tr = Trainer(cfg, model, acc)
+        losses = []
+        for step in range(6):
+            batch = to_dev(g.fwd_batch())
+            if step % 2:
+                V = int(g.cfg['n_items'])
+                batch['item_id'] = (batch['item_id'] % (V - 1)) + 1
+            losses.append(float(tr.train_step(batch)))
+        torch.cuda.synchronize()
+        assert bool(getattr(tr, '_graphs', {})) == bool(use_graph)
+        if use_graph:
+            assert all('graph' in v for v in tr._graphs.values())
+        results.append((losses, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}))
+    (l1, s1), (l0, s0) = results
+    # same kernels in the same order; split-K / bias-gradient reductions use float atomics, so runs agree to round-off only
+    assert max(abs(a - b) for a, b in zip(l1, l0)) < 1e-5 * max(abs(x) for x in l0), (l1, l0)
+    for k in s0:
+        if k.endswith('key.bias'):
+            continue
+        assert rel_err(s1[k], s0[k]) < 1e-4, (k, rel_err(s1[k], s0[k]))

@@ -37,7 +37,7 @@ SIGNATURES = {
     'ur_count_positive_i32': 'plpp',
     'ur_loss_finish_f32': 'plpfppp',
     'ur_rowlist_link': 'ppillpppl' + 'p',
-    'ur_rowlist_apply_f32': 'pppi' + 'pppp' + 'l' + 'plpl' + 'l' + 'plpl' + 'i' + 'fffff' + 'ppp' + 'p' + 'p',
+    'ur_rowlist_apply_f32': 'pppi' + 'pppp' + 'l' + 'plpl' + 'l' + 'plpl' + 'i' + 'fffff' + 'ppp' + 'p' + 'ppi' + 'p',
     'ur_dense_opt_f32': 'ppppl' + 'i' + 'fffff' + 'ppp' + 'p',
     'ur_sqnorm_accum_f32': 'plpp',
     'ur_clip_coef_f32': 'pfpp',

@@ -64,14 +64,18 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
                                                             int32_t* __restrict__ head, const int32_t* __restrict__ next,
                                                             const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq,
                                                             RowSource s0, int32_t n0, RowSource s1, int mode, OptHyper h,
-                                                            float* __restrict__ sqnorm_out) {
+                                                            float* __restrict__ sqnorm_out, const int32_t* __restrict__ u_begin_dev,
+                                                            const int32_t* __restrict__ u_end_dev) {
     constexpr int LPR = D4 < 32 ? D4 : 32;
     constexpr int VPL = D4 / LPR;
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31, sub = lane / LPR, col = lane % LPR;
     const int64_t group0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
     const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x >> 5) * RPW;
-    const int nu = *n_uniq;
+    // [u_begin, u_end) of the unique-row list (device-resident bounds; default: the whole list).  Used to update the rows that
+    // only the scorer touches while the encoder backward is still producing the gradients of the history rows.
+    const int ub = u_begin_dev ? *u_begin_dev : 0;
+    const int nu = u_end_dev ? *u_end_dev : *n_uniq;
     const bool skip = h.skip_flag && *h.skip_flag != 0;
     const float gs = h.grad_scale_dev ? *h.grad_scale_dev : 1.f;
     float bc1 = 1.f, bc2s = 1.f;
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
     float sq = 0.f;
     const bool is_adam = (mode == OPT_ADAM || mode == OPT_ADAMW);
     const bool update = (mode != OPT_SQNORM) && !skip;
-    for (int64_t u = group0; u < nu; u += ngroups) {
+    for (int64_t u = ub + group0; u < nu; u += ngroups) {
         const int64_t id = uniq[u];
         int32_t e = head[id];
         // Issue the parameter / moment loads FIRST: they do not depend on the list walk, so their HBM latency overlaps
@@ -222,21 +226,26 @@ int ur_rowlist_apply_f32(float* table, float* mom, float* var, int d, int32_t* h
                          int64_t coef0_group, int64_t n0, const float* src1, int64_t src1_group, const float* coef1,
                          int64_t coef1_group, int mode, float lr, float beta1, float beta2, float eps, float weight_decay,
                          const int32_t* step_dev, const float* grad_scale_dev, const int32_t* skip_flag, float* sqnorm_out,
-                         void* stream) {
+                         const int32_t* u_begin_dev, const int32_t* u_end_dev, int small_ctas, void* stream) {
     if (d <= 0 || (d & 3) || mode < 0 || mode > 3) return UR_ERR_BAD_ARG;
     if (max_uniq == 0) return UR_OK;
     ur::RowSource s0{src0, coef0, src0_group > 0 ? src0_group : 1, coef0_group > 0 ? coef0_group : 1};
     ur::RowSource s1{src1, coef1, src1_group > 0 ? src1_group : 1, coef1_group > 0 ? coef1_group : 1};
     ur::OptHyper h{lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale_dev, skip_flag};
     const int rpw = d >= 128 ? 1 : 128 / d;
-    int64_t blocks = (max_uniq + 8 * rpw - 1) / (8 * rpw);
-    const int64_t cap = (int64_t)ur::kNumSMs * 16;
+    // small_ctas: 128-thread CTAs (6 K registers) that fit next to a resident persistent GEMM CTA when this launch runs on a
+    // side stream concurrently with the encoder backward
+    const int threads = small_ctas ? 128 : 256;
+    const int wpc = threads / 32;
+    int64_t blocks = (max_uniq + wpc * rpw - 1) / (wpc * rpw);
+    const int64_t cap = (int64_t)ur::kNumSMs * (small_ctas ? 32 : 16);
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
 #define UR_CASE(D)                                                                                                        \
     case D:                                                                                                               \
-        ur::rowlist_apply_kernel<D / 4><<<(unsigned)blocks, 256, 0, st>>>((float4*)table, (float4*)mom, (float4*)var, head, next, \
-                                                                          uniq, n_uniq, s0, (int32_t)n0, s1, mode, h, sqnorm_out); \
+        ur::rowlist_apply_kernel<D / 4><<<(unsigned)blocks, threads, 0, st>>>((float4*)table, (float4*)mom, (float4*)var, head,   \
+                                                                              next, uniq, n_uniq, s0, (int32_t)n0, s1, mode, h,    \
+                                                                              sqnorm_out, u_begin_dev, u_end_dev);                 \
         break;
     switch (d) {
         UR_CASE(4) UR_CASE(16) UR_CASE(32) UR_CASE(64) UR_CASE(128) UR_CASE(256) UR_CASE(512)

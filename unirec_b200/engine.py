@@ -84,6 +84,8 @@ class RowGrad:
         self.next = None
         self.uniq = None
         self.n_uniq = None
+        self.n_hist = None         # early-link mode: number of unique rows touched by the history keys (linked first)
+        self.early = False         # this step's lists were linked ahead of the backward pass (Engine._early_link)
         self.specs = []            # list of (keys, src, src_group, coef, coef_group)
         self.linked = False
         self.pad_id = 0            # key value that is skipped (global padding id; -1 for localized shard keys)
@@ -91,6 +93,20 @@ class RowGrad:
     def reset(self):
         self.specs = []
         self.linked = False
+        self.early = False
+
+    def prepare(self, n):
+        """Allocate / size the list state for a step with n entries."""
+        dev = self.param.device
+        V = self.param.shape[0]
+        if self.head is None or self.head.numel() != V:
+            self.head = torch.full((V,), -1, dtype=torch.int32, device=dev)
+        if self.next is None or self.next.numel() < n:
+            self.next = torch.empty(n, dtype=torch.int32, device=dev)
+            self.uniq = torch.empty(n, dtype=torch.int32, device=dev)
+        if self.n_uniq is None:
+            self.n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.n_hist = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def add(self, keys, src, src_group=1, coef=None, coef_group=1):
         if len(self.specs) >= 2:
@@ -104,16 +120,7 @@ class RowGrad:
         """Thread the batch entries onto per-row lists (idempotent within a step)."""
         if self.linked or not self.specs:
             return
-        dev = self.param.device
-        V = self.param.shape[0]
-        n = self.n_entries()
-        if self.head is None or self.head.numel() != V:
-            self.head = torch.full((V,), -1, dtype=torch.int32, device=dev)
-        if self.next is None or self.next.numel() < n:
-            self.next = torch.empty(n, dtype=torch.int32, device=dev)
-            self.uniq = torch.empty(n, dtype=torch.int32, device=dev)
-        if self.n_uniq is None:
-            self.n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.prepare(self.n_entries())
         self.n_uniq.zero_()
         off = 0
         for keys, *_ in self.specs:
@@ -501,6 +508,12 @@ class Engine:
         self.dense_table_grads = False      # exact-dense mode (reference autograd semantics)
         self.nan_flag = None
         self.last = None
+        # stream-level overlap of the table update with the encoder backward (set up by the Trainer, see _early_link)
+        self.overlap_hook = None          # FusedOptimizer (provides early_apply) or None
+        self.overlap_mode = 1             # 1: link the row lists on a side stream during the forward pass;
+                                          # 2: also update the target-only rows on the side stream during the backward pass
+        self._side = None
+        self._ev_main = self._ev_link = None
 
     # ---- setup ------------------------------------------------------------------------------
     def table_for_seq(self):
@@ -560,6 +573,39 @@ class Engine:
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._rowgrads = {}
 
+    # ---- overlap of the row-sparse table update with the encoder (single-table sequence towers) ----
+    def _overlap_rowgrad(self):
+        """The RowGrad eligible for early linking, or None.  Eligible: a Trainer enabled it, plain (unsharded) engine, SASRec/GRU
+        tower (history and targets index the same table), row-sparse updates."""
+        if self.overlap_hook is None or type(self) is not Engine or self.tower_kind not in ('sasrec', 'gru'):
+            return None
+        if self.model.table_update == 'dense' or not self.model.training:
+            return None
+        return self.rowgrad(self.table_for_target())
+
+    def _early_link(self, rg, item_id, item_seq):
+        """Both key sets of the step are known before the forward pass: thread them onto the per-row lists on a side stream while
+        the encoder runs.  History keys go first, so uniq[0:n_hist) are the rows whose gradient needs the encoder backward and
+        uniq[n_hist:n_uniq) are touched by the scorer only -- FusedOptimizer.early_apply updates the latter right after the
+        loss kernel, concurrently with the backward pass."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ev_main = torch.cuda.Event()
+            self._ev_link = torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        self._ev_main.record(main)                      # the previous step's update of head/next/uniq is complete
+        self._side.wait_event(self._ev_main)
+        n_target, n_hist = item_id.numel(), item_seq.numel()
+        with torch.cuda.stream(self._side):
+            rg.prepare(n_target + n_hist)
+            rg.n_uniq.zero_()
+            ops.rowlist_link(rg.head, item_seq, n_target, rg.next, rg.uniq, rg.n_uniq, pad_id=rg.pad_id)
+            rg.n_hist.copy_(rg.n_uniq)
+            ops.rowlist_link(rg.head, item_id, 0, rg.next, rg.uniq, rg.n_uniq, pad_id=rg.pad_id)
+            self._ev_link.record(self._side)
+        rg.linked = True
+        rg.early = True
+
     # ---- sequence-row hooks (overridden by the row-sharded engine) -------------------------------
     def seq_rows_source(self, item_seq):
         """(table, index) such that table[index] are the history rows of the local batch."""
@@ -601,6 +647,9 @@ class Engine:
         B, N = item_id.shape
         for rg in self._rowgrads.values():
             rg.reset()
+        early_rg = self._overlap_rowgrad()
+        if early_rg is not None:
+            self._early_link(early_rg, item_id, item_seq)
         user = self.tower.forward(item_seq=item_seq, item_seq_len=item_seq_len, user_id=user_id, save=True)
         loss_type = m.loss_type
         scores = ws.get('scores', (B, N))
@@ -626,6 +675,8 @@ class Engine:
         else:
             ops.loss_finish(loss_vec, loss, denom_host=float(B), nan_flag=self.nan_flag)
         self.last = dict(user=user, item_id=item_id, user_id=user_id, dscore=dscore, grad_user=grad_user, B=B, N=N)
+        if early_rg is not None and self.overlap_mode >= 2:
+            self.overlap_hook.early_apply(self, early_rg, [(user, N, dscore, 1, B * N), (user, 1, None, 1, item_seq.numel())])
         out_loss = loss if reduction else loss_vec.clone()
         return out_loss, (scores if want_scores else None), user
 

@@ -30,6 +30,7 @@ class FusedOptimizer(torch.optim.Optimizer):
         self.mode = _KERNEL_MODES[opt_type]
         self.max_grad_norm = None
         self._st = None
+        self._early = None          # (RowGrad, event) of the early table update issued for the current step
 
     # ---- state ----------------------------------------------------------------------------------
     def _state(self):
@@ -61,6 +62,32 @@ class FusedOptimizer(torch.optim.Optimizer):
         for p in self.model._engine.table_params():
             p.grad = None
 
+    # ---- early table update (overlaps the encoder backward) -------------------------------------
+    def _hyper(self, st, scale=None):
+        g = self.param_groups[0]
+        (b1, b2) = g['betas']
+        return dict(lr=g['lr'], beta1=b1, beta2=b2, eps=g['eps'], weight_decay=g['weight_decay'], step_dev=st['step'],
+                    grad_scale_dev=scale, skip_flag=self.model._engine.nan_flag)
+
+    @torch.no_grad()
+    def early_apply(self, eng, rg, sources):
+        """Called by the engine right after the loss kernel when the step's row lists were linked early: rows touched only by the
+        targets/negatives (uniq[n_hist:]) have their complete gradient already (dL/ds x user embedding), so they are updated now,
+        on the side stream, while the main stream runs the encoder backward.  step() later updates uniq[:n_hist]."""
+        st = self._state()
+        ts = self._table_state(st, rg.param)
+        main = torch.cuda.current_stream()
+        ev = eng._ev_main
+        ev.record(main)                                # loss kernel + NaN flag are complete
+        eng._side.wait_event(ev)
+        with torch.cuda.stream(eng._side):
+            ops.step_advance(st['step'], eng.nan_flag)
+            ops.rowlist_apply(rg.param.data, ts.get('m'), ts.get('v'), rg.head, rg.next, rg.uniq, rg.n_uniq, sources[0][4],
+                              sources, self.mode, u_begin=rg.n_hist, small_ctas=True, **self._hyper(st))
+            done = torch.cuda.Event()
+            done.record(eng._side)
+        self._early = (rg, done)
+
     # ---- step -----------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None):
@@ -71,6 +98,17 @@ class FusedOptimizer(torch.optim.Optimizer):
         skip = eng.nan_flag
         dense_tables = self.model.table_update == 'dense'
         rowgrads = [rg for rg in eng.rowgrads() if rg.specs]
+        early_rg = None
+        for rg in rowgrads:
+            if rg.early:                    # lists were linked on the side stream during the forward pass
+                torch.cuda.current_stream().wait_event(eng._ev_link)
+        if self._early is not None:
+            early_rg, done = self._early
+            self._early = None
+            torch.cuda.current_stream().wait_event(done)
+            if self.max_grad_norm is not None or dense_tables:
+                raise RuntimeError('early table update is incompatible with gradient clipping / dense table updates '
+                                   '(the Trainer disables it in those configurations)')
         dense_grads = {}
         if dense_tables:
             for rg in rowgrads:
@@ -78,7 +116,8 @@ class FusedOptimizer(torch.optim.Optimizer):
         else:
             for rg in rowgrads:
                 rg.link()
-        ops.step_advance(st['step'], skip)
+        if early_rg is None:
+            ops.step_advance(st['step'], skip)      # (already advanced by early_apply otherwise)
 
         scale = None
         if self.max_grad_norm is not None:
@@ -108,7 +147,11 @@ class FusedOptimizer(torch.optim.Optimizer):
                               ts.get('v').view(-1) if 'v' in ts else None, self.mode, **hyper)
             else:
                 rg = eng.rowgrad(p)
-                if rg.specs:
+                if rg.specs and rg is early_rg:
+                    # remaining rows: the ones the history touches (their lists may also hold target entries)
+                    ops.rowlist_apply(p.data, ts.get('m'), ts.get('v'), rg.head, rg.next, rg.uniq, rg.n_uniq,
+                                      rg.specs[1][0].numel(), rg.sources(), self.mode, u_end=rg.n_hist, **hyper)
+                elif rg.specs:
                     ops.rowlist_apply(p.data, ts.get('m'), ts.get('v'), rg.head, rg.next, rg.uniq, rg.n_uniq, rg.n_entries(),
                                       rg.sources(), self.mode, **hyper)
         for rg in rowgrads:

@@ -49,11 +49,11 @@ class Trainer(object):
         self.best_valid_score = None
         self.start_epoch = 0
         self.cur_step = 1
+        gcv = config.get('grad_clip_value', None)
+        self.grad_clip_value = gcv if gcv is not None and gcv > 0 else None
         self.optimizer = self._build_optimizer(config['optimizer'], self.model)
         self.scheduler = self._build_scheduler(config['scheduler'], config['scheduler_factor'])
         self.model, self.optimizer, self.scheduler = self.accelerator.prepare(self.model, self.optimizer, self.scheduler)
-        gcv = config.get('grad_clip_value', None)
-        self.grad_clip_value = gcv if gcv is not None and gcv > 0 else None
         self.evaluator = None
         self.user_history = None
         self.tb_logger = None
@@ -64,7 +64,14 @@ class Trainer(object):
         rmsprop fall back to torch.optim over dense gradients (requires table_update=dense)."""
         if opt_type in ('adam', 'adamw', 'sgd', 'sparse_adam'):
             model._ur_fast_grads = True
-            return FusedOptimizer(model, opt_type, lr=self.learning_rate, weight_decay=self.weight_decay)
+            opt = FusedOptimizer(model, opt_type, lr=self.learning_rate, weight_decay=self.weight_decay)
+            # overlap the row-sparse table update with the encoder backward (engine._early_link / optim.early_apply)
+            mode = int(self.config.get('overlap_table_update', 0))
+            if mode and not self.accelerator.distributed and hasattr(model, '_engine'):
+                model._engine.overlap_hook = opt
+                # mode 2 (early update of the target-only rows) needs the final gradient scale up front: no clipping
+                model._engine.overlap_mode = mode if self.grad_clip_value is None else 1
+            return opt
         if model.table_update != 'dense':
             raise ValueError("optimizer %r runs through torch.optim and needs dense table gradients: set table_update='dense'"
                              % (opt_type,))
@@ -122,8 +129,94 @@ class Trainer(object):
                 dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
                 flat.grad.div_(self.accelerator.num_processes)
 
+    def device_batches(self, batches, depth=2):
+        """Iterate host batches (dicts or tuples of CPU tensors) as device batches, copying batch i+1 to the GPU on a copy
+        stream while step i computes (pinned memory makes the copy asynchronous).  Device-resident batches pass through.
+        The reference gets the same effect from accelerate's prepared DataLoader moving tensors ahead of the step
+        (trainer.py:261)."""
+        dev = self.accelerator.device
+        if dev.type != 'cuda':
+            yield from batches
+            return
+        copy_stream = getattr(self, '_copy_stream', None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
+
+        def to_dev(b):
+            with torch.cuda.stream(copy_stream):
+                if isinstance(b, dict):
+                    out = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()}
+                else:
+                    out = type(b)(v.to(dev, non_blocking=True) if torch.is_tensor(v) else v for v in b)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return out, ev
+
+        queue = []
+        it = iter(batches)
+        for b in it:
+            queue.append(to_dev(b))
+            if len(queue) >= depth:
+                break
+        while queue:
+            out, ev = queue.pop(0)
+            torch.cuda.current_stream().wait_event(ev)
+            for v in (out.values() if isinstance(out, dict) else out):
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(torch.cuda.current_stream())
+            nxt = next(it, None)
+            if nxt is not None:
+                queue.append(to_dev(nxt))
+            yield out
+
     def train_step(self, samples):
-        """One iteration of the hot loop (reference: trainer.py:327-357) without host synchronisation."""
+        """One iteration of the hot loop (reference: trainer.py:327-357) without host synchronisation.  After two eager
+        iterations per batch signature the whole step (forward, loss, backward, table + encoder update) is captured into a CUDA
+        graph and replayed: ~45 kernel launches and the Python glue collapse into one graph launch."""
+        g = self._graph_for(samples)
+        if g is None:
+            return self._eager_step(samples)
+        for k, v in g['static'].items():
+            v.copy_(samples[k], non_blocking=True)
+        g['graph'].replay()
+        return g['loss'].clone()
+
+    # ---- CUDA-graph plumbing ------------------------------------------------------------------
+    def _graph_for(self, samples):
+        from unirec_b200 import ops
+        from unirec_b200.engine import Engine
+        model = self.accelerator.unwrap_model(self.model)
+        eng = getattr(model, '_engine', None)
+        if (not int(self.config.get('cuda_graph', 1)) or self.accelerator.distributed or type(eng) is not Engine
+                or not isinstance(self.optimizer, FusedOptimizer) and not isinstance(getattr(self.optimizer, 'optimizer', None), FusedOptimizer)
+                or ops.PROFILE is not None or ops.TIMED_OP is not None or eng.overlap_hook is not None):
+            return None
+        tensors = {k: v for k, v in samples.items() if torch.is_tensor(v)}
+        if not tensors or any(not v.is_cuda for v in tensors.values()) or len(tensors) != len(samples):
+            return None
+        pg = self.optimizer.param_groups[0]
+        key = (tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items())),
+               pg['lr'], pg['weight_decay'], tuple(pg['betas']), pg['eps'], self.grad_clip_value, model.training)
+        cache = self.__dict__.setdefault('_graphs', {})
+        g = cache.get(key)
+        if g is None:
+            if len(cache) >= 8:                 # a stream of ever-changing shapes (or learning rates) stays eager
+                return None
+            g = cache[key] = {'seen': 0}
+        if 'graph' in g:
+            return g
+        g['seen'] += 1
+        if g['seen'] <= 2:                      # eager warm-up: sizes the workspace, the row lists and the optimizer state
+            return None
+        static = {k: v.clone() for k, v in tensors.items()}
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._eager_step(static)
+        g.update(graph=graph, static=static, loss=loss)
+        return g
+
+    def _eager_step(self, samples):
         model = self.model
         model.train()
         loss, _, _, _ = model(**samples)
@@ -174,7 +267,7 @@ class Trainer(object):
             t0 = time.time()
             total = None
             flag = self.accelerator.unwrap_model(self.model)._engine
-            for batch_idx, inter_data in enumerate(train_data):
+            for batch_idx, inter_data in enumerate(self.device_batches(train_data)):
                 samples = {k: inter_data[v] for k, v in key2index.items()}
                 loss = self.train_step(samples)
                 if self.accelerator.distributed:

@@ -233,7 +233,8 @@ def rowlist_link(head, keys, entry_offset, nxt, uniq, n_uniq, pad_id=0):
 
 
 def rowlist_apply(table, mom, var, head, nxt, uniq, n_uniq, max_uniq, sources, mode, lr=0.0, beta1=0.9, beta2=0.999,
-                  eps=1e-8, weight_decay=0.0, step_dev=None, grad_scale_dev=None, skip_flag=None, sqnorm_out=None):
+                  eps=1e-8, weight_decay=0.0, step_dev=None, grad_scale_dev=None, skip_flag=None, sqnorm_out=None,
+                  u_begin=None, u_end=None, small_ctas=False):
     """sources: list of 1 or 2 tuples (src, src_group, coef_or_None, coef_group, n_entries)."""
     s0 = sources[0]
     s1 = sources[1] if len(sources) > 1 else (None, 1, None, 1, 0)
@@ -242,7 +243,9 @@ def rowlist_apply(table, mom, var, head, nxt, uniq, n_uniq, max_uniq, sources, m
           _f32(s0[0]), s0[1], _f32(s0[2]), s0[3], s0[4], _f32(s1[0]), s1[1], _f32(s1[2]), s1[3],
           OPT_CODES[mode], float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
           _ptr(step_dev, torch.int32) if step_dev is not None else None, _f32(grad_scale_dev),
-          _ptr(skip_flag, torch.int32) if skip_flag is not None else None, _f32(sqnorm_out), _stream())
+          _ptr(skip_flag, torch.int32) if skip_flag is not None else None, _f32(sqnorm_out),
+          _ptr(u_begin, torch.int32) if u_begin is not None else None,
+          _ptr(u_end, torch.int32) if u_end is not None else None, int(small_ctas), _stream())
 
 
 def dense_opt(param, grad, mom, var, mode, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step_dev=None,
