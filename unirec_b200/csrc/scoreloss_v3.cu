@@ -37,8 +37,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // LR = lanes per row in the dot phase (each lane owns UPL = d/(4 LR) float4 of the row), KW = warps per CTA
-template <int D, int LOSS, int LR, int KW, int KS>     // KS = ring stages per warp
-__global__ void __launch_bounds__(KW * 32, 2) score_loss_v3_kernel(const ScoreLossParams p) {
+template <int D, int LOSS, int LR, int KW, int KS, int MINB>     // KS = ring stages per warp, MINB = resident CTAs per SM
+__global__ void __launch_bounds__(KW * 32, MINB) score_loss_v3_kernel(const ScoreLossParams p) {
     constexpr int D4 = D / 4;
     constexpr int UPL = D4 / LR;             // float4 per lane in the dot phase
     constexpr int RPC = 32 / LR;             // rows per chunk
@@ -323,16 +323,16 @@ static size_t smem_bytes(int N) {
            (size_t)((N + 15) & ~15) + 128;
 }
 
-template <int D, int LR, int KW, int KS>
+template <int D, int LR, int KW, int KS, int MINB = 2>
 static int launch(const ScoreLossParams& p, int loss_type, cudaStream_t st) {
     const size_t sm = smem_bytes<D, LR, KW, KS>(p.N);
-    if (sm > 112 * 1024) return UR_ERR_UNSUPPORTED;      // 2 CTAs per SM
+    if (sm > (size_t)(227 * 1024) / MINB - 1024) return UR_ERR_UNSUPPORTED;      // MINB CTAs per SM (1 KB reserved per CTA)
     if (loss_type == 0) {
-        cudaFuncSetAttribute(score_loss_v3_kernel<D, 0, LR, KW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        score_loss_v3_kernel<D, 0, LR, KW, KS><<<(unsigned)p.B, KW * 32, sm, st>>>(p);
+        cudaFuncSetAttribute(score_loss_v3_kernel<D, 0, LR, KW, KS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        score_loss_v3_kernel<D, 0, LR, KW, KS, MINB><<<(unsigned)p.B, KW * 32, sm, st>>>(p);
     } else {
-        cudaFuncSetAttribute(score_loss_v3_kernel<D, 1, LR, KW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        score_loss_v3_kernel<D, 1, LR, KW, KS><<<(unsigned)p.B, KW * 32, sm, st>>>(p);
+        cudaFuncSetAttribute(score_loss_v3_kernel<D, 1, LR, KW, KS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        score_loss_v3_kernel<D, 1, LR, KW, KS, MINB><<<(unsigned)p.B, KW * 32, sm, st>>>(p);
     }
     return UR_OK;
 }
@@ -355,6 +355,11 @@ int score_loss_v3_try(const ScoreLossParams& p, int d, int loss_type, cudaStream
             if (var == 0) return v3::launch<128, 2, 4, 3>(p, loss_type, st);
             if (var == 1) return v3::launch<128, 4, 8, 3>(p, loss_type, st);
             if (var == 2) return v3::launch<128, 2, 3, 4>(p, loss_type, st);
+            // single-wave shapes: 7 small CTAs per SM hold all of B <= 1036 samples at once (no tail wave)
+            if (var == 4) { const int rc = v3::launch<128, 4, 2, 2, 7>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 5) { const int rc = v3::launch<128, 2, 1, 2, 7>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 6) { const int rc = v3::launch<128, 4, 2, 2, 4>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 7) { const int rc = v3::launch<128, 2, 2, 2, 5>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
             return v3::launch<128, 2, 6, 2>(p, loss_type, st);
         case 256: return v3::launch<256, 4, 6, 2>(p, loss_type, st);
         case 512: return v3::launch<512, 8, 6, 2>(p, loss_type, st);
