@@ -132,6 +132,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--gemm-precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='keep Trainer.train_step eager (ncu launch lists)')
     ap.add_argument('--overlap', type=int, default=0, help='overlap_table_update mode (0 off, 1 early link, 2 + early update)')
     args = ap.parse_args()
     sys.argv = sys.argv[:1]
@@ -159,7 +160,7 @@ def main():
     cfg_args.update({k: v for k, v in w.items() if k not in ('K', 'B')})
     cfg_args.update(batch_size=B, n_sample_neg_train=K, gemm_precision=args.gemm_precision, epochs=1,
                     output_path=os.path.join(ROOT, 'gpurun_out', 'bench_ckpt'), table_shard_world=world,
-                    overlap_table_update=args.overlap)
+                    overlap_table_update=args.overlap, cuda_graph=0 if args.no_graph else 1)
     cfg = argument_parser.parse_arguments(cfg_args, argv=[])
     cfg['device'] = dev
     general.init_seed(2022)
@@ -251,6 +252,9 @@ def main():
     samples = B * world * args.steps
     value = samples / (ms_total / 1e3)
     algo_bytes = B * (1 + K) * d * 4                     # target/negative rows read once by the fused score kernel
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed `ncu --set full` capture
+    # (profiles/r01c_full_captures.csv: 542.5 MB + 9.8 MB); only known for the default workload on one GPU
+    traffic = 552.3e6 if (args.workload == DEFAULT_WORKLOAD and world == 1) else None
     k_ms = statistics.mean(kernel_ms) if kernel_ms else float('nan')
     achieved = algo_bytes / (k_ms / 1e3) / 1e9
     line = {
@@ -270,7 +274,7 @@ def main():
                                      'eagerly so that the roofline kernel can be bracketed by CUDA events)'},
         'roofline': {'kernel': 'score_loss_kernel (fused gather+dot+softmax+grad)' if world == 1 else
                      'score_partial_kernel (owner-side gather+dot+partial softmax, row-sharded table)', 'bound': 'hbm', 'achieved': achieved,
-                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None, 'peak_kind': peak_kind,
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_kind': peak_kind,
                      'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': k_ms},
         'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
     }

@@ -37,6 +37,14 @@ CASES = {
     'sasrec_softmax_d128': dict(model='SASRec', n_items=301, n_users=11, embedding_size=128, hidden_size=128,
                                 n_layers=1, n_heads=2, inner_size=256, max_seq_len=50, loss_type='softmax',
                                 K=16, B=4, hidden_act='swish', init_std=0.1),
+    # padding edge cases of the data path (adduserhistory.py:45-51 'unorder' masking zeroes history items in place, :60-68 can cut
+    # the history to length 0): a sequence with no real item, a pad at the output position L-1, pads between real items
+    'sasrec_softmax_padedges': dict(model='SASRec', n_items=211, n_users=37, embedding_size=32, hidden_size=32,
+                                    n_layers=2, n_heads=2, inner_size=64, max_seq_len=8, loss_type='softmax',
+                                    K=5, B=8, init_std=0.2, edge=1),
+    'sasrec_bpr_nopos_padedges': dict(model='SASRec', n_items=157, n_users=29, embedding_size=64, hidden_size=64,
+                                      n_layers=2, n_heads=4, inner_size=96, max_seq_len=11, loss_type='bpr',
+                                      use_position_emb=0, hidden_act='gelu', K=3, B=8, init_std=0.2, edge=1),
     'gru_bpr': dict(model='GRU', n_items=123, n_users=19, embedding_size=32, hidden_size=64,
                     max_seq_len=7, loss_type='bpr', K=5, B=6, init_std=0.3),
     'gru_softmax_h32': dict(model='GRU', n_items=99, n_users=19, embedding_size=32, hidden_size=32,
@@ -53,7 +61,7 @@ CASES = {
 }
 
 
-def make_batch(cfg, B, K, L, gen):
+def make_batch(cfg, B, K, L, gen, edge=False):
     V, U = cfg['n_items'], cfg['n_users']
     user_id = torch.randint(1, U, (B,), generator=gen, dtype=torch.int64)
     item_id = torch.randint(1, V, (B, 1 + K), generator=gen, dtype=torch.int64)
@@ -74,6 +82,15 @@ def make_batch(cfg, B, K, L, gen):
         item_seq[b, L - n:] = torch.randint(1, V, (n,), generator=gen, dtype=torch.int64).to(torch.int32)
     if B > 2 and L > 1:
         item_seq[2, L - 1] = item_id[2, 0].to(torch.int32)
+    if edge:
+        item_seq[3, :] = 0                 # empty history
+        lens[3] = 0
+        item_seq[4, L - 4:] = torch.randint(1, V, (4,), generator=gen, dtype=torch.int64).to(torch.int32)
+        item_seq[4, L - 1] = 0             # pad at the output position, real items before it
+        lens[4] = 4
+        item_seq[5, L - 5:] = torch.randint(1, V, (5,), generator=gen, dtype=torch.int64).to(torch.int32)
+        item_seq[5, L - 3] = 0             # pad between real items
+        lens[5] = 5
     return dict(user_id=user_id, item_id=item_id, label=label, item_seq=item_seq, item_seq_len=lens)
 
 
@@ -82,9 +99,13 @@ def main():
     from unirec.utils import argument_parser, general
     os.makedirs(OUT, exist_ok=True)
     saved_argv, sys.argv = sys.argv, sys.argv[:1]
+    only = set(saved_argv[1:])
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         case = dict(case)
         B, K = case.pop('B'), case.pop('K')
+        edge = bool(case.pop('edge', 0))
         args = dict(BASE)
         args.update(case)
         cfg = argument_parser.parse_arguments(args)
@@ -95,7 +116,7 @@ def main():
         model.train()
         L = int(cfg['max_seq_len'])
         gen = torch.Generator().manual_seed(seed + 1)
-        batch = make_batch(cfg, B, K, L, gen)
+        batch = make_batch(cfg, B, K, L, gen, edge)
         if cfg['model'] == 'MF':
             fwd_batch = {k: batch[k] for k in ('user_id', 'item_id', 'label')}
         else:

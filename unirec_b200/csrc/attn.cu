@@ -42,19 +42,22 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
         if (valid) atomicMin(&s_jlo, j);
     }
     __syncthreads();
-    // Exact work skipping (results identical to the dense reference computation):
-    //  * a padded QUERY row never reaches the loss (only real positions feed the last position through unmasked keys), so its
-    //    context is written as zeros instead of a softmax over all-masked keys;
-    //  * for a real query row at least one key is unmasked, hence every masked key has weight exp(-10000 + ...) == 0 in fp32:
-    //    keys before the first real item and (causal) keys after the query are skipped.
-    const int j_lo = s_jlo;
+    // Exact work skipping (results identical to the dense reference computation; the mask depends on KEYS only, sasrec.py:40-57):
+    //  * a padded query row other than L-1 never reaches the loss (as a key it is masked in the next layer, and only row L-1 of
+    //    the last layer feeds the scorer), so its context is written as zeros.  Row L-1 is always computed, padded or not;
+    //  * when the query sees at least one unmasked key, every masked key has weight exp(-10000 + ...) == 0 in fp32: keys before
+    //    the first real item and (causal) keys after the query are skipped;
+    //  * a sequence without any real item (empty history): every key carries the same -10000, which cancels in the softmax ->
+    //    all keys participate (j_lo = 0).
+    const bool none_valid = s_jlo == L;        // then every position is live: all rows feed the next layer's keys
+    const int j_lo = none_valid ? 0 : s_jlo;
 
     const int q_begin = q_only_last ? L - 1 : blockIdx.y * q_tile;
     const int q_end = q_only_last ? L : min(L, q_begin + q_tile);
     float* pw = pbuf + warp * Lp;
     float* qw = qbuf + warp * DH;
     for (int i = q_begin + warp; i < q_end; i += 8) {
-        if (madd[i] != 0.f) {                       // padded query row: dead output, keep it finite
+        if (madd[i] != 0.f && i != L - 1 && !none_valid) {   // padded query row (not the output position): dead, keep it finite
 #pragma unroll
             for (int r = 0; r < CPL; ++r) {
                 const int c = lane + 32 * r;
@@ -63,7 +66,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
             if (lane == 0) lse[((int64_t)b * H + h) * L + i] = 0.f;
             continue;
         }
-        const int j_hi = causal ? i : L - 1;        // inclusive
+        // (no real key anywhere: future keys carry the same -10000 as the padded ones, so the row attends to all L keys)
+        const int j_hi = (causal && !none_valid) ? i : L - 1;        // inclusive
         for (int c = lane; c < DH; c += 32) qw[c] = __ldg(base + (int64_t)i * 3 * d + c);
         __syncwarp();
         float mx = -INFINITY;
@@ -75,7 +79,9 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
                 const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * KS + c);
                 dot += f4_dot(q4, k4);
             }
-            const float s = dot * scale + madd[j];
+            // two roundings like the reference (scores / sqrt(d_h), then + mask): with every key masked the sum lands on the
+            // 1e-3 grid of fp32 near -10000 and a fused multiply-add would round differently
+            const float s = __fadd_rn(__fmul_rn(dot, scale), madd[j]);
             pw[j] = s;
             mx = fmaxf(mx, s);
         }
@@ -169,10 +175,11 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
         __syncthreads();
         // ---- phase A ----  (same exact skipping as the forward kernel: padded query rows have dctx == 0 and contribute
         //                     nothing; masked keys have P == 0 for real query rows)
-        const int j_lo = s_jlo;
+        const bool none_valid = s_jlo == L;        // then every position is live: all rows feed the next layer's keys
+    const int j_lo = none_valid ? 0 : s_jlo;
         for (int ii = warp; ii < nq; ii += 8) {
             const int i = q0 + ii;
-            if (madd[i] != 0.f) {                      // padded query row: dQ = 0, no dK/dV contribution
+            if (madd[i] != 0.f && i != L - 1 && !none_valid) {   // dead padded query row: dQ = 0, no dK/dV contribution
 #pragma unroll
                 for (int r = 0; r < CPL; ++r) {
                     const int c = lane + 32 * r;
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
                 }
                 continue;
             }
-            const int j_hi = causal ? i : L - 1;
+            const int j_hi = (causal && !none_valid) ? i : L - 1;
             const int64_t row = (int64_t)b * L + i;
             float dsum = 0.f;
             for (int c = lane; c < DH; c += 32) dsum = fmaf(dOs[ii * DH + c], __ldg(ctx + row * d + h * DH + c), dsum);
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
                     dot += f4_dot(q4, k4);
                     dp += f4_dot(g4, v4);
                 }
-                const float p = __expf(dot * scale + madd[j] - lse_i);
+                const float p = __expf(__fadd_rn(__fmul_rn(dot, scale), madd[j]) - lse_i);
                 Ps[ii * Lp + j] = p;
                 dSs[ii * Lp + j] = p * (dp - Di) * scale;
             }
@@ -226,8 +233,8 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
             const int j = warp + 8 * k;
             if (j < L && j >= j_lo) {
                 // rows that wrote P/dS for this key: real query rows, and (causal) only rows i >= j
-                for (int ii = causal ? max(0, j - q0) : 0; ii < nq; ++ii) {
-                    if (madd[q0 + ii] != 0.f) continue;
+                for (int ii = (causal && !none_valid) ? max(0, j - q0) : 0; ii < nq; ++ii) {
+                    if (madd[q0 + ii] != 0.f && q0 + ii != L - 1 && !none_valid) continue;
                     const float ds = dSs[ii * Lp + j], p = Ps[ii * Lp + j];
 #pragma unroll
                     for (int r = 0; r < CPL; ++r) {

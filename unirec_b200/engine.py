@@ -22,18 +22,20 @@ PRECISION_CODES = {'fp32': 0, 'tf32': 1, 'bf16': 2, 'tf32x3': 3}
 
 
 class Workspace:
-    """Named device buffers, reallocated only when a shape changes (static shapes -> CUDA-graph friendly)."""
+    """Named device buffers, one per (name, shape, dtype).  A buffer is never freed or moved once handed out: captured CUDA
+    graphs (Trainer.train_step) keep raw pointers into it, and train / eval / last-partial-batch shapes alternate."""
 
     def __init__(self, device):
         self.device = device
-        self.buf: Dict[str, torch.Tensor] = {}
+        self.buf: Dict[tuple, torch.Tensor] = {}
 
     def get(self, name, shape, dtype=torch.float32, zero=False):
         shape = tuple(int(s) for s in shape)
-        t = self.buf.get(name)
-        if t is None or t.shape != shape or t.dtype != dtype:
+        key = (name, shape, dtype)
+        t = self.buf.get(key)
+        if t is None:
             t = torch.empty(shape, dtype=dtype, device=self.device)
-            self.buf[name] = t
+            self.buf[key] = t
         if zero:
             t.zero_()
         return t
@@ -102,6 +104,8 @@ class RowGrad:
         if self.head is None or self.head.numel() != V:
             self.head = torch.full((V,), -1, dtype=torch.int32, device=dev)
         if self.next is None or self.next.numel() < n:
+            if self.next is not None:          # captured CUDA graphs may still point at the smaller buffers: keep them alive
+                self.__dict__.setdefault('_retired', []).append((self.next, self.uniq))
             self.next = torch.empty(n, dtype=torch.int32, device=dev)
             self.uniq = torch.empty(n, dtype=torch.int32, device=dev)
         if self.n_uniq is None:
