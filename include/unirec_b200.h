@@ -49,21 +49,23 @@ int ur_pool_sum_fwd_f32(const float* table, int d, const int32_t* item_seq, int6
 /* ---- K1+K3: Y = LayerNorm(table[item_seq] + pos[0..L-1]); saves per-row mean / rstd.
  * replaces: SASRec.forward_user_emb prologue, unirec/model/sequential/sasrec.py:60-69 */
 int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos /*nullable*/, const float* gamma, const float* beta, float eps,
-                           const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd, void* stream);
+                           const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd,
+                           const int32_t* tok_src /*nullable*/, const int32_t* n_tok_dev /*nullable*/, void* stream);
 /* dX[B*L,d] = gradient wrt the gathered rows (feeds the row-sparse table update); dgamma/dbeta/dpos are ACCUMULATED */
 int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* gamma, const int32_t* item_seq, int64_t B, int L,
                            int d, const float* mean, const float* rstd, const float* dY, float* dX, float* dgamma, float* dbeta,
-                           float* dpos /*nullable*/, void* stream);
+                           float* dpos /*nullable*/, const int32_t* tok_inv /*nullable*/, void* stream);
 
 /* ---- K6: post-LN residual.  X <- X + R (kept for backward), Y = LayerNorm(X).
  * replaces: LayerNorm(hidden + input) unirec/model/modules.py:314, :353 */
 int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R /*nullable*/, int64_t ldr, const float* gamma, const float* beta,
-                      float eps, int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd, void* stream);
+                      float eps, int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd,
+                      const int32_t* rows_dev /*nullable*/, void* stream);
 /* dZ = LN'(Z) (dY + dExtra); dgamma/dbeta ACCUMULATED; dZ may alias dY; dzsum (nullable) += column sums of dZ, i.e. the
  * bias gradient of the linear layer whose output (plus residual) is Z */
 int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const float* mean, const float* rstd, const float* dY,
                       int64_t lddy, const float* dExtra /*nullable*/, int64_t ldde, int64_t rows, int d, float* dZ, int64_t lddz,
-                      float* dgamma, float* dbeta, float* dzsum /*nullable*/, void* stream);
+                      float* dgamma, float* dbeta, float* dzsum /*nullable*/, const int32_t* rows_dev /*nullable*/, void* stream);
 
 /* ---- K4/K7: C (+)= act(op(A) op(B) + bias); preact (nullable) receives the pre-activation for backward.
  * replaces: nn.Linear calls unirec/model/modules.py:285-287,312,348-351; gru.py:30-31
@@ -85,24 +87,42 @@ int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
 /* ur_gemm_f32 with two fused epilogue stages (csrc/gemm_tc.cu; unfused SIMT route otherwise):
  *   dact   (nullable): C = (op(A) op(B)) * act'(dact[row, col])      -- replaces: autograd of the FFN activation, modules.py:348-351
  *   colsum (nullable): colsum[col] += sum_rows C[row, col]           -- the bias gradient of the layer that consumes C as dy
- * precision 3 = 3xTF32 split (hi/lo operand split in shared memory, fp32-class results from the tensor pipe). */
+ * precision 3 = 3xTF32 split (hi/lo operand split in shared memory, fp32-class results from the tensor pipe).
+ * rows_dev (nullable): device-resident live token count of the packed sequence layout (ur_pack_tokens); the launch is sized for
+ *   the static M / K and the kernels stop at the live count, so no host synchronisation is needed. */
 int ur_gemm_fused_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                       int64_t ldb, float* C, int64_t ldc, const float* bias /*nullable*/, int act, float* preact /*nullable*/,
                       int64_t ldp, int accumulate, int precision, const float* dact /*nullable*/, int64_t ldd,
-                      float* colsum /*nullable*/, void* stream);
+                      float* colsum /*nullable*/, const int32_t* rows_dev /*nullable*/, int rows_dim, void* stream);
+/* exact-fp32 kernel with the same device-resident token count (rows_dim 1: M = min(M, *rows_dev); 2: K = min(K, *rows_dev)) */
+int ur_gemm_simt_rows_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                          int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
+                          const int32_t* rows_dev, int rows_dim, void* stream);
 /* out[c][r] = in[r][c] for small weight matrices (dx = dy W is issued as an NT product on W^T) */
 int ur_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
 /* dY *= act'(preact) */
 int ur_act_bwd_f32(float* dY, const float* preact, int64_t n, int act, void* stream);
 /* out[n] += sum_m X[m,n] (bias gradients) */
-int ur_colsum_accum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* stream);
+int ur_colsum_accum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, const int32_t* rows_dev /*nullable*/, void* stream);
 
 /* ---- K5: fused attention on packed QKV [B*L, 3d] with the SASRec additive mask (-10000), L <= 256.
  * replaces: MultiHeadAttention.forward unirec/model/modules.py:289-311 and SASRec._get_attention_mask sasrec.py:40-57 */
+/* offs / tok_src (nullable, both or none): packed token layout of ur_pack_tokens (sample b owns rows [offs[b], offs[b+1]) of qkv / ctx).
+ * q_last (nullable, with q_only_last): the single query per sample comes from a compact [B, d] buffer, ctx / dctx are compact
+ * [B, d] too and dQ goes to dq_last [B, d]. */
 int ur_attn_fwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
-                    float* ctx, float* lse /*[B,H,L]*/, void* stream);
+                    float* ctx, float* lse /*[B,H,L]*/, const int32_t* offs, const int32_t* tok_src, const float* q_last, void* stream);
 int ur_attn_bwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
-                    const float* ctx, const float* lse, const float* dctx, float* dqkv, void* stream);
+                    const float* ctx, const float* lse, const float* dctx, float* dqkv, const int32_t* offs, const int32_t* tok_src,
+                    const float* q_last, float* dq_last, void* stream);
+
+/* ---- token packing for the sequence towers (csrc/pack.cu): live positions = real items + position L-1 (+ every position of a
+ * sequence without real items).  replaces: nothing in the reference -- it computes all B*L positions (sasrec.py:59-76); the dead ones
+ * cannot reach the loss.  keep_all = 1 yields the identity map. */
+int ur_pack_tokens(const int32_t* item_seq, int64_t B, int L, int keep_all, int32_t* offs /*[B+1]*/, int32_t* tok_src /*[B*L]*/,
+                   int32_t* tok_inv /*[B*L]*/, int32_t* last_tok /*[B]*/, int32_t* n_tok /*[1]*/, void* stream);
+/* zero rows [*n_dev, roundup32(*n_dev)) of X[rows_cap, width] */
+int ur_zero_tail_rows_f32(float* X, int64_t ld, int width, const int32_t* n_dev, int64_t rows_cap, void* stream);
 
 /* ---- K9: GRU cell pointwise parts (matrix products go through ur_gemm_f32).
  * replaces: nn.GRU inside GRU.forward_user_emb unirec/model/sequential/gru.py:30 */

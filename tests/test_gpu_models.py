@@ -208,6 +208,25 @@ def test_trainer_fit_loop_and_checkpoint(tmp_path):
     assert set(model2.state_dict()) == set(model.state_dict())
 
 
+@pytest.mark.parametrize('name', ['sasrec_softmax', 'sasrec_softmax_padedges', 'sasrec_bpr_nopos_padedges', 'sasrec_softmax_d128'])
+@pytest.mark.parametrize('pack,trim', [(0, 1), (1, 0), (0, 0)])
+def test_sasrec_packing_and_trimming_do_not_change_results(name, pack, trim):
+    """pack_sequences / trim_last_layer only remove dead work: every combination must reproduce the reference goldens (the default
+    1/1 combination is what every other test runs)."""
+    g = Golden(name)
+    model, _ = cuda_model(g, table_update='dense', pack_sequences=pack, trim_last_layer=trim)
+    model.train()
+    loss, scores, user_emb, _ = model(**to_dev(g.fwd_batch()), return_loss_only=False)
+    assert abs(float(loss) - float(g.loss)) <= TOL * abs(float(g.loss))
+    assert rel_err(scores.cpu(), g.scores) < TOL and rel_err(user_emb.cpu(), g.user_emb) < TOL
+    loss.backward()
+    scale = max(float(v.abs().max()) for v in g.grads.values())
+    for k, p in model.named_parameters():
+        ref = g.grads[k]
+        err = float((p.grad.cpu().double() - ref.double()).abs().max())
+        assert err <= TOL * max(float(ref.abs().max()), 1e-2 * scale), (k, err)
+
+
 @pytest.mark.parametrize('trim', [1, 0])
 def test_sasrec_d128_3xtf32_tensor_core_path_meets_fp32_bar(trim):
     """gemm_precision=tf32x3 (the bench default): tcgen05 GEMMs with the hi/lo operand split -> the fp32 parity bar (1e-3) holds,

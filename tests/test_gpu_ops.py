@@ -467,3 +467,37 @@ def test_transpose_small():
     out = torch.empty(128, 384, device=DEV)
     ops.transpose(w.to(DEV), out)
     assert torch.equal(out.cpu(), w.t().contiguous())
+
+
+def test_pack_tokens_map():
+    """Live positions = real items + position L-1; a sequence without real items keeps every position (csrc/pack.cu)."""
+    from unirec_b200 import ops
+    g = gen(31)
+    B, L = 1500, 13          # > 1024 samples: exercises the multi-round block scan
+    seq = torch.randint(1, 50, (B, L), generator=g, dtype=torch.int32)
+    lens = torch.randint(0, L + 1, (B,), generator=g)
+    seq = torch.where(torch.arange(L)[None, :] >= (L - lens)[:, None], seq, torch.zeros_like(seq))
+    seq[3, L - 1] = 0                      # pad at the output position
+    seq[5, L - 3] = 0                      # pad between real items
+    seq[7] = 0                             # empty history
+    real = seq > 0
+    keep = real.clone()
+    keep[:, L - 1] = True
+    keep |= ~real.any(1, keepdim=True)
+    ref_src = torch.nonzero(keep.flatten()).flatten().to(torch.int32)
+    n_ref = int(keep.sum())
+    offs, src, inv = (torch.empty(B + 1, dtype=torch.int32, device=DEV), torch.full((B * L,), -7, dtype=torch.int32, device=DEV),
+                      torch.empty(B * L, dtype=torch.int32, device=DEV))
+    last, n = torch.empty(B, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.pack_tokens(seq.to(DEV), offs, src, inv, last, n)
+    assert int(n) == n_ref and int(offs[B]) == n_ref
+    assert torch.equal(src[:n_ref].cpu(), ref_src)
+    cnt = keep.sum(1)
+    assert torch.equal(offs[:B].cpu().long(), torch.cumsum(cnt, 0) - cnt)
+    assert torch.equal(last.cpu().long(), torch.cumsum(cnt, 0) - 1)
+    inv_ref = torch.full((B * L,), -1, dtype=torch.int32)
+    inv_ref[ref_src.long()] = torch.arange(n_ref, dtype=torch.int32)
+    assert torch.equal(inv.cpu(), inv_ref)
+    ops.pack_tokens(seq.to(DEV), offs, src, inv, last, n, keep_all=True)
+    assert int(n) == B * L and torch.equal(src.cpu(), torch.arange(B * L, dtype=torch.int32))
+    assert torch.equal(last.cpu().long(), torch.arange(B) * L + L - 1)

@@ -18,19 +18,22 @@ SIGNATURES = {
     'ur_gather_rows_f32': 'plipilpp',
     'ur_scatter_add_rows_f32': 'plipilplpllp',
     'ur_pool_sum_fwd_f32': 'piplipfppppp',
-    'ur_seq_prep_ln_fwd_f32': 'ppppfpliipppp',
-    'ur_seq_prep_ln_bwd_f32': 'pppplii' + 'ppp' + 'pppp' + 'p',
-    'ur_add_ln_fwd_f32': 'plplppflipl' + 'ppp',
-    'ur_add_ln_bwd_f32': 'plppp' + 'pl' + 'pl' + 'li' + 'pl' + 'pppp',
+    'ur_seq_prep_ln_fwd_f32': 'ppppfpliippp' + 'pp' + 'p',
+    'ur_seq_prep_ln_bwd_f32': 'pppplii' + 'ppp' + 'pppp' + 'p' + 'p',
+    'ur_add_ln_fwd_f32': 'plplppflipl' + 'pp' + 'p' + 'p',
+    'ur_add_ln_bwd_f32': 'plppp' + 'pl' + 'pl' + 'li' + 'pl' + 'ppp' + 'p' + 'p',
     'ur_gemm_f32': 'iilllplplplpipliip',
     'ur_gemm_simt_f32': 'iilllplplplpiplip',
     'ur_gemm_tc_f32': 'iilllplplplpipliip',
-    'ur_gemm_fused_f32': 'iilllplplplpipliiplpp',
+    'ur_gemm_fused_f32': 'iilllplplplpipliiplp' + 'pi' + 'p',
+    'ur_gemm_simt_rows_f32': 'iilllplplplpipli' + 'pi' + 'p',
+    'ur_pack_tokens': 'pliipppppp',
+    'ur_zero_tail_rows_f32': 'plipl' + 'p',
     'ur_transpose_f32': 'pllpp',
     'ur_act_bwd_f32': 'pplip',
-    'ur_colsum_accum_f32': 'plllpp',
-    'ur_attn_fwd_f32': 'ppliiiiippp',
-    'ur_attn_bwd_f32': 'ppliiiii' + 'ppppp',
+    'ur_colsum_accum_f32': 'plllp' + 'p' + 'p',
+    'ur_attn_fwd_f32': 'ppliiiiipp' + 'ppp' + 'p',
+    'ur_attn_bwd_f32': 'ppliiiii' + 'pppp' + 'pppp' + 'p',
     'ur_gru_gate_fwd_f32': 'plppppli' + 'p',
     'ur_gru_gate_bwd_f32': 'pppplppli' + 'p',
     'ur_score_loss_fwd_bwd_f32': 'pipplipppp' + 'ffipf' + 'pppp' + 'p',

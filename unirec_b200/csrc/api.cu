@@ -8,8 +8,8 @@ extern "C" int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int6
 
 extern "C" int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                              int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp,
-                             int accumulate, int precision, const float* dact, int64_t ldd, float* colsum, void* stream)
-    __attribute__((weak));
+                             int accumulate, int precision, const float* dact, int64_t ldd, float* colsum,
+                             const int32_t* rows_dev, int rows_dim, void* stream) __attribute__((weak));
 
 extern "C" {
 
@@ -30,22 +30,24 @@ int ur_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const f
 
 int ur_gemm_fused_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                       int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
-                      int precision, const float* dact, int64_t ldd, float* colsum, void* stream) {
+                      int precision, const float* dact, int64_t ldd, float* colsum, const int32_t* rows_dev, int rows_dim,
+                      void* stream) {
     if (dact && (accumulate || preact)) return UR_ERR_BAD_ARG;
     if (precision != 0 && ur_gemm_tc_ex) {
         const int rc = ur_gemm_tc_ex(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, accumulate, precision,
-                                     dact, ldd, colsum, stream);
+                                     dact, ldd, colsum, rows_dev, rows_dim, stream);
         if (rc != UR_ERR_UNSUPPORTED) return rc;
     }
     // unfused route: exact GEMM, then the activation derivative and the column sums as separate launches
-    int rc = ur_gemm_simt_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, dact ? 0 : act, preact, ldp, accumulate, stream);
+    int rc = ur_gemm_simt_rows_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, dact ? 0 : act, preact, ldp, accumulate,
+                                   rows_dev, rows_dim, stream);
     if (rc != UR_OK) return rc;
     if (dact) {
         if (ldc != N || ldd != N) return UR_ERR_UNSUPPORTED;
         rc = ur_act_bwd_f32(C, dact, M * N, act, stream);
         if (rc != UR_OK) return rc;
     }
-    if (colsum) rc = ur_colsum_accum_f32(C, ldc, M, N, colsum, stream);
+    if (colsum) rc = ur_colsum_accum_f32(C, ldc, M, N, colsum, rows_dim == 1 ? rows_dev : nullptr, stream);
     return rc;
 }
 

@@ -11,22 +11,28 @@ namespace ur {
 constexpr float kMaskAdd = -10000.f;
 
 template <int DH>
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq, int L, int H,
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq, int Lmax, int H,
                                                        float scale, int causal, int q_tile, int q_only_last,
-                                                       float* __restrict__ ctx, float* __restrict__ lse) {
+                                                       float* __restrict__ ctx, float* __restrict__ lse,
+                                                       const int32_t* __restrict__ offs, const int32_t* __restrict__ tok_src,
+                                                       const float* __restrict__ q_last) {
     constexpr int KS = DH + 4;               // padded row stride: conflict-free float4 reads with lanes over keys
     constexpr int CPL = (DH + 31) / 32;      // output columns per lane
     extern __shared__ __align__(16) float smem[];
-    float* Ks = smem;                        // [L][KS]
-    float* Vs = Ks + (size_t)L * KS;         // [L][KS]
-    const int Lp = (L + 3) & ~3;             // keeps every sub-buffer 16-byte aligned
-    float* madd = Vs + (size_t)L * KS;       // [Lp]
+    float* Ks = smem;                        // [Lmax][KS]
+    float* Vs = Ks + (size_t)Lmax * KS;      // [Lmax][KS]
+    const int Lp = (Lmax + 3) & ~3;          // keeps every sub-buffer 16-byte aligned
+    float* madd = Vs + (size_t)Lmax * KS;    // [Lp]
     float* pbuf = madd + Lp;                 // [8][Lp]
     float* qbuf = pbuf + 8 * Lp;             // [8][DH]
     const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
     const int d = H * DH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* base = qkv + (int64_t)b * L * 3 * d + h * DH;
+    // packed mode (csrc/pack.cu): the sample owns rows [offs[b], offs[b+1]) of qkv / ctx, its live positions in order (the last
+    // one is position L-1); row j is the position tok_src[row0 + j].  Unpacked: rows b*L .. b*L+L-1.
+    const int64_t row0 = offs ? (int64_t)offs[b] : (int64_t)b * Lmax;
+    const int L = offs ? offs[b + 1] - offs[b] : Lmax;       // live positions of this sample (>= 1)
+    const float* base = qkv + row0 * 3 * d + h * DH;
 
     for (int i = threadIdx.x; i < L * (DH / 4); i += blockDim.x) {
         const int j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
@@ -37,7 +43,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
     if (threadIdx.x == 0) s_jlo = L;
     __syncthreads();
     for (int j = threadIdx.x; j < L; j += blockDim.x) {
-        const bool valid = seq[(int64_t)b * L + j] > 0;
+        const bool valid = seq[tok_src ? (int64_t)tok_src[row0 + j] : row0 + j] > 0;
         madd[j] = valid ? 0.f : kMaskAdd;
         if (valid) atomicMin(&s_jlo, j);
     }
@@ -54,6 +60,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
 
     const int q_begin = q_only_last ? L - 1 : blockIdx.y * q_tile;
     const int q_end = q_only_last ? L : min(L, q_begin + q_tile);
+    // q_only_last with q_last != null: the query comes from the compact [B, d] buffer and the context goes to row b of ctx
+    const bool compact = q_only_last && q_last != nullptr;
     float* pw = pbuf + warp * Lp;
     float* qw = qbuf + warp * DH;
     for (int i = q_begin + warp; i < q_end; i += 8) {
@@ -61,14 +69,15 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
 #pragma unroll
             for (int r = 0; r < CPL; ++r) {
                 const int c = lane + 32 * r;
-                if (c < DH) ctx[((int64_t)b * L + i) * d + h * DH + c] = 0.f;
+                if (c < DH) ctx[(row0 + i) * d + h * DH + c] = 0.f;
             }
-            if (lane == 0) lse[((int64_t)b * H + h) * L + i] = 0.f;
+            if (lane == 0) lse[((int64_t)b * H + h) * Lmax + i] = 0.f;
             continue;
         }
         // (no real key anywhere: future keys carry the same -10000 as the padded ones, so the row attends to all L keys)
         const int j_hi = (causal && !none_valid) ? i : L - 1;        // inclusive
-        for (int c = lane; c < DH; c += 32) qw[c] = __ldg(base + (int64_t)i * 3 * d + c);
+        for (int c = lane; c < DH; c += 32)
+            qw[c] = compact ? __ldg(q_last + (int64_t)b * d + h * DH + c) : __ldg(base + (int64_t)i * 3 * d + c);
         __syncwarp();
         float mx = -INFINITY;
         for (int j = j_lo + lane; j <= j_hi; j += 32) {
@@ -109,9 +118,9 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
 #pragma unroll
         for (int r = 0; r < CPL; ++r) {
             const int c = lane + 32 * r;
-            if (c < DH) ctx[((int64_t)b * L + i) * d + h * DH + c] = o[r] * inv;
+            if (c < DH) ctx[(compact ? (int64_t)b : row0 + i) * d + h * DH + c] = o[r] * inv;
         }
-        if (lane == 0) lse[((int64_t)b * H + h) * L + i] = mx + __logf(sum);
+        if (lane == 0) lse[((int64_t)b * H + h) * Lmax + i] = mx + __logf(sum);
         __syncwarp();
     }
 }
@@ -120,18 +129,20 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
 // recomputes P, forms dS and writes dQ; phase B (warp per key, exclusive ownership -> no atomics) accumulates
 // dK and dV in registers across all tiles.
 template <int DH, int KPW>   // KPW = max keys owned per warp = ceil(L / 8); register cap scales with it
-__global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) attn_bwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq, int L, int H,
+__global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) attn_bwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq, int Lmax, int H,
                                                           float scale, int causal, int q_only_last, const float* __restrict__ ctx,
                                                           const float* __restrict__ lse, const float* __restrict__ dctx,
-                                                          float* __restrict__ dqkv) {
+                                                          float* __restrict__ dqkv, const int32_t* __restrict__ offs,
+                                                          const int32_t* __restrict__ tok_src, const float* __restrict__ q_last,
+                                                          float* __restrict__ dq_last) {
     constexpr int KS = DH + 4;
     constexpr int CPL = (DH + 31) / 32;
     constexpr int QT = 32;
     extern __shared__ __align__(16) float smem[];
-    float* Ks = smem;                        // [L][KS]
-    float* Vs = Ks + (size_t)L * KS;         // [L][KS]
-    const int Lp = (L + 3) & ~3;
-    float* madd = Vs + (size_t)L * KS;       // [Lp]
+    float* Ks = smem;                        // [Lmax][KS]
+    float* Vs = Ks + (size_t)Lmax * KS;      // [Lmax][KS]
+    const int Lp = (Lmax + 3) & ~3;
+    float* madd = Vs + (size_t)Lmax * KS;    // [Lp]
     float* Ps = madd + Lp;                   // [QT][Lp]
     float* dSs = Ps + QT * Lp;               // [QT][Lp]  (already multiplied by scale)
     float* Qs = dSs + QT * Lp;               // [QT][DH]
@@ -139,8 +150,11 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
     const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
     const int d = H * DH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* base = qkv + (int64_t)b * L * 3 * d + h * DH;
-    float* dbase = dqkv + (int64_t)b * L * 3 * d + h * DH;
+    const int64_t row0 = offs ? (int64_t)offs[b] : (int64_t)b * Lmax;     // packed mode: see attn_fwd_kernel
+    const int L = offs ? offs[b + 1] - offs[b] : Lmax;
+    const bool compact = q_only_last && q_last != nullptr;               // q / ctx / dctx / dq in compact [B, d] buffers
+    const float* base = qkv + row0 * 3 * d + h * DH;
+    float* dbase = dqkv + row0 * 3 * d + h * DH;
 
     for (int i = threadIdx.x; i < L * (DH / 4); i += blockDim.x) {
         const int j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
@@ -151,7 +165,7 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
     if (threadIdx.x == 0) s_jlo = L;
     __syncthreads();
     for (int j = threadIdx.x; j < L; j += blockDim.x) {
-        const bool valid = seq[(int64_t)b * L + j] > 0;
+        const bool valid = seq[tok_src ? (int64_t)tok_src[row0 + j] : row0 + j] > 0;
         madd[j] = valid ? 0.f : kMaskAdd;
         if (valid) atomicMin(&s_jlo, j);
     }
@@ -168,8 +182,10 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
         __syncthreads();   // previous tile fully consumed (and K/V/madd visible on the first pass)
         for (int i = threadIdx.x; i < nq * (DH / 4); i += blockDim.x) {
             const int ii = i / (DH / 4), c = (i - ii * (DH / 4)) * 4;
-            const int64_t row = (int64_t)b * L + q0 + ii;
-            *reinterpret_cast<float4*>(Qs + ii * DH + c) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(q0 + ii) * 3 * d + c));
+            const int64_t row = compact ? (int64_t)b : row0 + q0 + ii;
+            *reinterpret_cast<float4*>(Qs + ii * DH + c) =
+                compact ? __ldg(reinterpret_cast<const float4*>(q_last + (int64_t)b * d + h * DH + c))
+                        : __ldg(reinterpret_cast<const float4*>(base + (int64_t)(q0 + ii) * 3 * d + c));
             *reinterpret_cast<float4*>(dOs + ii * DH + c) = __ldg(reinterpret_cast<const float4*>(dctx + row * d + h * DH + c));
         }
         __syncthreads();
@@ -188,11 +204,11 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
                 continue;
             }
             const int j_hi = (causal && !none_valid) ? i : L - 1;
-            const int64_t row = (int64_t)b * L + i;
+            const int64_t row = compact ? (int64_t)b : row0 + i;
             float dsum = 0.f;
             for (int c = lane; c < DH; c += 32) dsum = fmaf(dOs[ii * DH + c], __ldg(ctx + row * d + h * DH + c), dsum);
             const float Di = warp_sum(dsum);
-            const float lse_i = lse[((int64_t)b * H + h) * L + i];
+            const float lse_i = lse[((int64_t)b * H + h) * Lmax + i];
             for (int j = j_lo + lane; j <= j_hi; j += 32) {
                 float dot = 0.f, dp = 0.f;
 #pragma unroll
@@ -223,7 +239,10 @@ __global__ void __launch_bounds__(256, (KPW <= 8 ? 3 : (KPW <= 16 ? 2 : 1))) att
 #pragma unroll
             for (int r = 0; r < CPL; ++r) {
                 const int c = lane + 32 * r;
-                if (c < DH) dbase[(int64_t)i * 3 * d + c] = dq[r];
+                if (c < DH) {
+                    if (compact) dq_last[(int64_t)b * d + h * DH + c] = dq[r];
+                    else dbase[(int64_t)i * 3 * d + c] = dq[r];
+                }
             }
         }
         __syncthreads();
@@ -280,7 +299,8 @@ extern "C" {
 // q_only_last: compute only query row L-1 (the last encoder layer feeds only [:, -1, :] into the scorer,
 // unirec/model/sequential/sasrec.py:74-75); all keys/values are still used.
 int ur_attn_fwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
-                    float* ctx, float* lse, void* stream) {
+                    float* ctx, float* lse, const int32_t* offs, const int32_t* tok_src, const float* q_last, void* stream) {
+    if ((offs == nullptr) != (tok_src == nullptr)) return UR_ERR_BAD_ARG;
     if (L <= 0 || L > 256 || H <= 0) return UR_ERR_BAD_ARG;
     if (B == 0) return UR_OK;
     const size_t smem = ur::attn_fwd_smem(L, dh);
@@ -293,7 +313,8 @@ int ur_attn_fwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L,
     case DH:                                                                                                           \
         if (smem > 48 * 1024)                                                                                          \
             cudaFuncSetAttribute(ur::attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        ur::attn_fwd_kernel<DH><<<grid, 256, smem, st>>>(qkv, item_seq, L, H, scale, causal, q_tile, q_only_last, ctx, lse); \
+        ur::attn_fwd_kernel<DH><<<grid, 256, smem, st>>>(qkv, item_seq, L, H, scale, causal, q_tile, q_only_last, ctx, lse,  \
+                                                         offs, tok_src, q_last);                                       \
         break;
     switch (dh) {
         UR_CASE(16) UR_CASE(32) UR_CASE(64) UR_CASE(128)
@@ -305,7 +326,9 @@ int ur_attn_fwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L,
 
 // dqkv must be zero-filled by the caller when q_only_last (only row L-1 of dQ is written).
 int ur_attn_bwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
-                    const float* ctx, const float* lse, const float* dctx, float* dqkv, void* stream) {
+                    const float* ctx, const float* lse, const float* dctx, float* dqkv, const int32_t* offs, const int32_t* tok_src,
+                    const float* q_last, float* dq_last, void* stream) {
+    if ((offs == nullptr) != (tok_src == nullptr) || (q_last == nullptr) != (dq_last == nullptr)) return UR_ERR_BAD_ARG;
     if (L <= 0 || L > 256 || H <= 0) return UR_ERR_BAD_ARG;
     if (B == 0) return UR_OK;
     const size_t smem = ur::attn_bwd_smem(L, dh);
@@ -317,7 +340,8 @@ int ur_attn_bwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L,
     do {                                                                                                                    \
         if (smem > 48 * 1024)                                                                                               \
             cudaFuncSetAttribute(ur::attn_bwd_kernel<DH, KPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        ur::attn_bwd_kernel<DH, KPW><<<grid, 256, smem, st>>>(qkv, item_seq, L, H, scale, causal, q_only_last, ctx, lse, dctx, dqkv); \
+        ur::attn_bwd_kernel<DH, KPW><<<grid, 256, smem, st>>>(qkv, item_seq, L, H, scale, causal, q_only_last, ctx, lse, dctx, dqkv, \
+                                                              offs, tok_src, q_last, dq_last);                                       \
     } while (0)
 #define UR_CASE(DH)                                           \
     case DH:                                                  \

@@ -38,13 +38,19 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
                                                         const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
                                                         const float* __restrict__ bias, int act, float* __restrict__ preact,
-                                                        int64_t ldp, int accumulate, int k_chunk) {
+                                                        int64_t ldp, int accumulate, int k_chunk,
+                                                        const int32_t* __restrict__ rows_dev, int rows_dim) {
+    if (rows_dev) {                // packed sequences: device-resident token count bounds the rows (1) or the reduction (2)
+        const int n = *rows_dev;
+        if (rows_dim == 1) M = min(M, n); else K = min(K, n);
+    }
     __shared__ __align__(16) float As[2][BK][BM];
     __shared__ __align__(16) float Bs[2][BK][BN];
     const int t = threadIdx.x;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * k_chunk;
     const int kend = min(K, kbeg + k_chunk);
+    if (m0 >= M) return;
     const int tx = t & 15, ty = t >> 4;
 
     float acc[8][8];
@@ -122,8 +128,10 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(float4* __restrict__ dY, c
 }
 
 // out[n] += sum_m X[m, n]   (bias gradients).  grid.x tiles columns by 128 (float4 x 32 lanes), grid.y splits rows.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int N, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int N, float* __restrict__ out,
+                                                     const int32_t* __restrict__ rows_dev) {
     __shared__ float4 sh[8][32];
+    if (rows_dev) M = min(M, (int64_t)*rows_dev);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = blockIdx.x * 128 + lane * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -143,9 +151,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 
 extern "C" {
 
-int ur_gemm_simt_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
-                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
-                     void* stream) {
+static int gemm_simt_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                            int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
+                            const int32_t* rows_dev, int rows_dim, void* stream) {
     if (M < 0 || N < 0 || K < 0 || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 3)) return UR_ERR_BAD_ARG;
     if (!transA && (K & 3)) return UR_ERR_BAD_ARG;      // A contiguous along k
     if (transA && (M & 3)) return UR_ERR_BAD_ARG;       // A contiguous along m
@@ -170,13 +178,27 @@ int ur_gemm_simt_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, co
     cudaStream_t st = (cudaStream_t)stream;
 #define UR_GEMM(TA, TB)                                                                                                   \
     ur::gemm_simt_kernel<TA, TB><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, \
-                                                       accumulate, (int)k_chunk)
+                                                       accumulate, (int)k_chunk, rows_dev, rows_dim)
     if (!transA && !transB) UR_GEMM(false, false);
     else if (!transA && transB) UR_GEMM(false, true);
     else if (transA && !transB) UR_GEMM(true, false);
     else UR_GEMM(true, true);
 #undef UR_GEMM
     UR_RETURN_LAST_ERROR();
+}
+
+int ur_gemm_simt_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
+                     void* stream) {
+    return gemm_simt_launch(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, accumulate, nullptr, 0, stream);
+}
+
+// same, with a device-resident token count (see ur_gemm_fused_f32)
+int ur_gemm_simt_rows_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                          int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
+                          const int32_t* rows_dev, int rows_dim, void* stream) {
+    if (rows_dev && rows_dim != 1 && rows_dim != 2) return UR_ERR_BAD_ARG;
+    return gemm_simt_launch(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, accumulate, rows_dev, rows_dim, stream);
 }
 
 int ur_act_bwd_f32(float* dY, const float* preact, int64_t n, int act, void* stream) {
@@ -189,14 +211,14 @@ int ur_act_bwd_f32(float* dY, const float* preact, int64_t n, int act, void* str
     UR_RETURN_LAST_ERROR();
 }
 
-int ur_colsum_accum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* stream) {
+int ur_colsum_accum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, const int32_t* rows_dev, void* stream) {
     if ((N & 3) || (ldx & 3)) return UR_ERR_BAD_ARG;
     if (M == 0 || N == 0) return UR_OK;
     int gy = (int)((M + 255) / 256);
     if (gy > 256) gy = 256;
     if (gy < 1) gy = 1;
     dim3 grid((unsigned)((N + 127) / 128), gy);
-    ur::colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, M, (int)N, out);
+    ur::colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, M, (int)N, out, rows_dev);
     UR_RETURN_LAST_ERROR();
 }
 

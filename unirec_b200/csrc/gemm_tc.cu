@@ -102,7 +102,9 @@ struct Params {
     int epi_bufs;           // store buffers per epilogue warp (1 or 2)
     int lo_stages;          // 3xTF32: depth of the lo ring
     int dbg_skip;           // bring-up: bit0 skip TMA store issue, bit1 skip bias, bit2 skip smem staging
-    int n_chunks, m_stripes, total_units;
+    int n_chunks, m_stripes, total_units, splits;
+    const int* rows_dev; int rows_dim;   // optional device-resident token count: rows_dim 1 -> M = min(M, *rows_dev) (row-parallel GEMMs),
+                                         // 2 -> K = min(K, *rows_dev) (token-reduction GEMMs; one operand has zero rows up to the next k-block)
     int dbg_lbo, dbg_sbo, dbg_kstep, dbg_major, dbg_layout;   // MN-major descriptor parameters (bytes / flags), tunable for bring-up
 };
 
@@ -208,7 +210,19 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
     uint64_t* tmem_full = lo_empty + SL;           // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    const int KB_all = (p.K + BK - 1) / BK;
+    int KB_all = (p.K + BK - 1) / BK;
+    int M_eff = p.M, m_stripes = p.m_stripes, kb_per_split = p.kb_per_split, total_units = p.total_units;
+    if (p.rows_dev) {                      // packed sequences: the live token count is only known on the device
+        const int n = *p.rows_dev;
+        if (p.rows_dim == 1) {
+            M_eff = min(p.M, n);
+            m_stripes = (M_eff + BM - 1) / BM;
+            total_units = m_stripes * p.n_chunks * p.splits;
+        } else {
+            KB_all = (min(p.K, n) + BK - 1) / BK;
+            kb_per_split = (KB_all + p.splits - 1) / p.splits;
+        }
+    }
     const uint32_t tmem_cols = 2 * NC;
 
     if (warp == 0 && lane == 0) {
@@ -236,16 +250,16 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
     auto decode = [&](int u, int& m0, int& n0, int& kb_begin, int& KB) {
         const int chunk = u % p.n_chunks;
         const int rest = u / p.n_chunks;
-        m0 = (rest % p.m_stripes) * BM;
+        m0 = (rest % m_stripes) * BM;
         n0 = chunk * NC;
-        kb_begin = (rest / p.m_stripes) * p.kb_per_split;
-        KB = min(KB_all - kb_begin, p.kb_per_split);
+        kb_begin = (rest / m_stripes) * kb_per_split;
+        KB = min(KB_all - kb_begin, kb_per_split);          // <= 0: nothing to do for this unit (every role skips it)
     };
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 int m0, n0, kb_begin, KB;
                 decode(u, m0, n0, kb_begin, KB);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -275,9 +289,10 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         if (lane == 0) {
             uint32_t it = 0, lt = 0;
             const uint32_t idesc = make_idesc(NC, kAmn ? p.dbg_major : 0, kBmn ? p.dbg_major : 0);
-            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++lt) {
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 int m0, n0, kb_begin, KB;
                 decode(u, m0, n0, kb_begin, KB);
+                if (KB <= 0) continue;
                 const uint32_t ab = lt & 1;
                 mbar_wait(tmem_empty + ab, ((lt >> 1) & 1) ^ 1);       // passes immediately for the first use of each buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -310,6 +325,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                     if (kSplit) umma_commit(lo_empty + (it % SL));
                 }
                 umma_commit(tmem_full + ab);         // accumulator complete
+                ++lt;
             }
         }
     } else if (warp < 2 + EPI_WARPS) {
@@ -347,9 +363,10 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
             ++nstore;
             return buf;
         };
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++lt) {
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             int m0, n0, kb_begin, KB;
             decode(u, m0, n0, kb_begin, KB);
+            if (KB <= 0) continue;
             const int row0 = m0 + lb * 32;
             const int64_t grow = min(row0 + lane, p.M - 1);       // clamp: out-of-range rows are clipped by the TMA store
             float4 dnext[8];
@@ -388,12 +405,13 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 const float* buf = emit(&tmC, v, p.accumulate != 0, ncol, row0);
                 if (p.colsum) {
                     // lane c sums column c of the staged chunk over this warp's (valid) rows: conflict-free transposed read
-                    const int nrows = min(32, p.M - row0);
+                    const int nrows = min(32, M_eff - row0);
                     float cs = 0.f;
                     for (int r = 0; r < nrows; ++r) cs += buf[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
                     atomicAdd(colsum_sm + ncol + lane, cs);
                 }
             }
+            ++lt;
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -402,7 +420,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         const int tid = threadIdx.x - (2 + EPI_WARPS) * 32;
         const int n4 = (int)(raw_bytes >> 4);
         uint32_t it = 0;
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             int m0, n0, kb_begin, KB;
             decode(u, m0, n0, kb_begin, KB);
             for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -500,8 +518,9 @@ int ur_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, vo
 // then uses the SIMT kernel (plus separate act_bwd / colsum launches).
 int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
                   float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate, int precision,
-                  const float* dact, int64_t ldd, float* colsum, void* stream) {
+                  const float* dact, int64_t ldd, float* colsum, const int32_t* rows_dev, int rows_dim, void* stream) {
     using namespace ur::tc;
+    if (rows_dev && rows_dim != 1 && rows_dim != 2) return UR_ERR_BAD_ARG;
     if (precision != 1 && precision != 3) return UR_ERR_UNSUPPORTED;
     const bool split3 = precision == 3;
     const bool a_mn = transA != 0;           // A stored [K, M]
@@ -564,7 +583,8 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     p.kb_per_split = kb_per_split; p.epi_bufs = epi_bufs; p.lo_stages = lo_stages;
     static const int env_skip = getenv("UR_TC_SKIP") ? atoi(getenv("UR_TC_SKIP")) : 0;
     p.dbg_skip = env_skip;
-    p.n_chunks = (int)(N / NC); p.m_stripes = (int)m_stripes; p.total_units = (int)(tiles * splits);
+    p.n_chunks = (int)(N / NC); p.m_stripes = (int)m_stripes; p.total_units = (int)(tiles * splits); p.splits = splits;
+    p.rows_dev = rows_dev; p.rows_dim = rows_dev ? rows_dim : 0;
     p.dbg_lbo = g_dbg_lbo; p.dbg_sbo = g_dbg_sbo; p.dbg_kstep = g_dbg_kstep; p.dbg_major = g_dbg_major; p.dbg_layout = g_dbg_layout;
     const unsigned grid = (unsigned)(p.total_units < ur::kNumSMs ? p.total_units : ur::kNumSMs);
     cudaStream_t st = (cudaStream_t)stream;
@@ -590,7 +610,7 @@ int ur_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
                    float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate, int precision,
                    void* stream) {
     return ur_gemm_tc_ex(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, accumulate, precision, nullptr, 0,
-                         nullptr, stream);
+                         nullptr, nullptr, 0, stream);
 }
 
 }  // extern "C"

@@ -53,13 +53,27 @@ __global__ void __launch_bounds__(256) seq_prep_ln_fwd_kernel(const float4* __re
                                                               const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                               float eps, const int32_t* __restrict__ seq, int64_t rows, int L, int d4,
                                                               float4* __restrict__ Y, float* __restrict__ mean_out,
-                                                              float* __restrict__ rstd_out) {
+                                                              float* __restrict__ rstd_out, const int32_t* __restrict__ tok_src,
+                                                              const int32_t* __restrict__ n_tok_dev) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t r = warp0; r < rows; r += nwarps) {
-        const int64_t id = __ldg(seq + r);
-        const int l = (int)(r % L);
+    // packed mode (csrc/pack.cu): output row t holds position tok_src[t]; rows [n_tok, roundup32(n_tok)) are written as zeros
+    // (the token-reduction GEMMs consume whole 32-row blocks)
+    const int64_t n_live = n_tok_dev ? min((int64_t)*n_tok_dev, rows) : rows;
+    const int64_t n_pad = n_tok_dev ? min(rows, (n_live + 31) & ~(int64_t)31) : rows;
+    for (int64_t r = warp0; r < n_pad; r += nwarps) {
+        if (r >= n_live) {
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                int c = lane + 32 * i;
+                if (c < d4) Y[r * d4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            continue;
+        }
+        const int64_t src = tok_src ? (int64_t)__ldg(tok_src + r) : r;
+        const int64_t id = __ldg(seq + src);
+        const int l = (int)(src % L);
         RowRegs<MAXV> x;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
@@ -147,7 +161,8 @@ __global__ void __launch_bounds__(256) seq_prep_ln_bwd_kernel(const float4* __re
                                                               int64_t B, int L, int d4, const float* __restrict__ mean_in,
                                                               const float* __restrict__ rstd_in, const float4* __restrict__ dY,
                                                               float4* __restrict__ dX, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta, float* __restrict__ dpos) {
+                                                              float* __restrict__ dbeta, float* __restrict__ dpos,
+                                                              const int32_t* __restrict__ tok_inv) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31;
     const int l = blockIdx.y;
@@ -157,6 +172,10 @@ __global__ void __launch_bounds__(256) seq_prep_ln_bwd_kernel(const float4* __re
     zero_regs(dgam); zero_regs(dbet); zero_regs(dp);
     for (int64_t b = warp0; b < B; b += nwarps) {
         const int64_t r = b * L + l;
+        // packed mode: dY / mean / rstd are indexed by the packed token, dX (the table-row gradient the optimizer reads by batch
+        // entry) keeps the [B*L, d] layout; dead positions carry no gradient and are never read (their key is the padding id)
+        const int64_t t = tok_inv ? (int64_t)__ldg(tok_inv + r) : r;
+        if (t < 0) continue;
         const int64_t id = __ldg(seq + r);
         RowRegs<MAXV> x, dy, dx;
 #pragma unroll
@@ -165,10 +184,10 @@ __global__ void __launch_bounds__(256) seq_prep_ln_bwd_kernel(const float4* __re
             if (c < d4) {
                 x.v[i] = ldg_stream(table + id * d4 + c);
                 if (pos) x.v[i] = f4_add(x.v[i], __ldg(pos + (int64_t)l * d4 + c));
-                dy.v[i] = dY[r * d4 + c];
+                dy.v[i] = dY[t * d4 + c];
             }
         }
-        ln_bwd_row<MAXV>(x, dy, d4, lane, mean_in[r], rstd_in[r], gamma, dx, dgam, dbet);
+        ln_bwd_row<MAXV>(x, dy, d4, lane, mean_in[t], rstd_in[t], gamma, dx, dgam, dbet);
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             int c = lane + 32 * i;
@@ -189,11 +208,24 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(float* __restrict__ X, int64_t ldx, const float* __restrict__ R, int64_t ldr,
                                                          const float4* __restrict__ gamma, const float4* __restrict__ beta, float eps,
                                                          int64_t rows, int d4, float* __restrict__ Y, int64_t ldy,
-                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                         const int32_t* __restrict__ rows_dev) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t r = warp0; r < rows; r += nwarps) {
+    // rows_dev: device-resident live row count (packed tokens); rows up to the next multiple of 32 are written as zeros
+    const int64_t n_live = rows_dev ? min((int64_t)*rows_dev, rows) : rows;
+    const int64_t n_pad = rows_dev ? min(rows, (n_live + 31) & ~(int64_t)31) : rows;
+    for (int64_t r = warp0; r < n_pad; r += nwarps) {
+        if (r >= n_live) {
+            float4* yr = reinterpret_cast<float4*>(Y + r * ldy);
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                int c = lane + 32 * i;
+                if (c < d4) yr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            continue;
+        }
         float4* xr = reinterpret_cast<float4*>(X + r * ldx);
         const float4* rr = R ? reinterpret_cast<const float4*>(R + r * ldr) : nullptr;
         RowRegs<MAXV> x;
@@ -219,14 +251,25 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
                                                          const float* dY, int64_t lddy, const float* __restrict__ dExtra, int64_t ldde,
                                                          int64_t rows, int d4, float* dZ, int64_t lddz,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                         float* __restrict__ dzsum) {
+                                                         float* __restrict__ dzsum, const int32_t* __restrict__ rows_dev) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     RowRegs<MAXV> dgam, dbet, dzs;
     zero_regs(dgam); zero_regs(dbet); zero_regs(dzs);
-    for (int64_t r = warp0; r < rows; r += nwarps) {
+    const int64_t n_live = rows_dev ? min((int64_t)*rows_dev, rows) : rows;
+    const int64_t n_pad = rows_dev ? min(rows, (n_live + 31) & ~(int64_t)31) : rows;
+    for (int64_t r = warp0; r < n_pad; r += nwarps) {
+        if (r >= n_live) {                         // zero tail: dZ is the token-reduction operand of the weight-gradient GEMM
+            float4* dzt = reinterpret_cast<float4*>(dZ + r * lddz);
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                int c = lane + 32 * i;
+                if (c < d4) dzt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            continue;
+        }
         const float4* zr = reinterpret_cast<const float4*>(Z + r * ldz);
         const float4* dyr = reinterpret_cast<const float4*>(dY + r * lddy);
         const float4* der = dExtra ? reinterpret_cast<const float4*>(dExtra + r * ldde) : nullptr;
@@ -271,7 +314,8 @@ static inline int ln_grid(int64_t rows) {
 extern "C" {
 
 int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* gamma, const float* beta, float eps,
-                           const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd, void* stream) {
+                           const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd,
+                           const int32_t* tok_src, const int32_t* n_tok_dev, void* stream) {
     if (d <= 0 || (d & 3)) return UR_ERR_BAD_ARG;
     const int64_t rows = B * L;
     if (rows == 0) return UR_OK;
@@ -280,7 +324,7 @@ int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* ga
 #define CALL(MV)                                                                                                    \
     ur::seq_prep_ln_fwd_kernel<MV><<<ur::ln_grid(rows), 256, 0, st>>>(                                              \
         (const float4*)table, (const float4*)pos, (const float4*)gamma, (const float4*)beta, eps, item_seq, rows, L, d4, \
-        (float4*)Y, mean, rstd);
+        (float4*)Y, mean, rstd, tok_src, n_tok_dev);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();
@@ -288,7 +332,7 @@ int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* ga
 
 int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* gamma, const int32_t* item_seq, int64_t B, int L,
                            int d, const float* mean, const float* rstd, const float* dY, float* dX, float* dgamma, float* dbeta,
-                           float* dpos, void* stream) {
+                           float* dpos, const int32_t* tok_inv, void* stream) {
     if (d <= 0 || (d & 3)) return UR_ERR_BAD_ARG;
     if (B * L == 0) return UR_OK;
     const int d4 = d / 4;
@@ -300,21 +344,21 @@ int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* ga
 #define CALL(MV)                                                                                               \
     ur::seq_prep_ln_bwd_kernel<MV><<<grid, 256, d * sizeof(float), st>>>(                                      \
         (const float4*)table, (const float4*)pos, (const float4*)gamma, item_seq, B, L, d4, mean, rstd,        \
-        (const float4*)dY, (float4*)dX, dgamma, dbeta, dpos);
+        (const float4*)dY, (float4*)dX, dgamma, dbeta, dpos, tok_inv);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();
 }
 
 int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R, int64_t ldr, const float* gamma, const float* beta, float eps,
-                      int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd, void* stream) {
+                      int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd, const int32_t* rows_dev, void* stream) {
     if (d <= 0 || (d & 3) || (ldx & 3) || (ldr & 3) || (ldy & 3)) return UR_ERR_BAD_ARG;
     if (rows == 0) return UR_OK;
     const int d4 = d / 4;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(MV)                                                                                                      \
     ur::add_ln_fwd_kernel<MV><<<ur::ln_grid(rows), 256, 0, st>>>(X, ldx, R, ldr, (const float4*)gamma, (const float4*)beta, \
-                                                                 eps, rows, d4, Y, ldy, mean, rstd);
+                                                                 eps, rows, d4, Y, ldy, mean, rstd, rows_dev);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();
@@ -322,7 +366,7 @@ int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R, int64_t ldr, const 
 
 int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const float* mean, const float* rstd, const float* dY,
                       int64_t lddy, const float* dExtra, int64_t ldde, int64_t rows, int d, float* dZ, int64_t lddz,
-                      float* dgamma, float* dbeta, float* dzsum, void* stream) {
+                      float* dgamma, float* dbeta, float* dzsum, const int32_t* rows_dev, void* stream) {
     if (d <= 0 || (d & 3) || (ldz & 3) || (lddy & 3) || (ldde & 3) || (lddz & 3)) return UR_ERR_BAD_ARG;
     if (rows == 0) return UR_OK;
     const int d4 = d / 4;
@@ -331,7 +375,7 @@ int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const flo
     if (grid > ur::kNumSMs * 2) grid = ur::kNumSMs * 2;   // fewer CTAs -> fewer column atomics
 #define CALL(MV)                                                                                                    \
     ur::add_ln_bwd_kernel<MV><<<grid, 256, d * sizeof(float), st>>>(Z, ldz, (const float4*)gamma, mean, rstd, dY, lddy, \
-                                                                    dExtra, ldde, rows, d4, dZ, lddz, dgamma, dbeta, dzsum);
+                                                                    dExtra, ldde, rows, d4, dZ, lddz, dgamma, dbeta, dzsum, rows_dev);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();

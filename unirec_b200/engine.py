@@ -34,7 +34,8 @@ class Workspace:
         key = (name, shape, dtype)
         t = self.buf.get(key)
         if t is None:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
+            # zero-filled once: rows beyond the live token count are read (never used) by whole-block kernels and must be finite
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
             self.buf[key] = t
         if zero:
             t.zero_()
@@ -149,19 +150,19 @@ def _lin_fwd(x, M, K, w, b, N, out, act=None, preact=None, lda=None, prec=0):
 
 
 def _lin_bwd(dy, M, N, x, K, w, dx, dw, db, lda_x=None, accumulate_dx=False, prec=0, lddy=None, lddx=None, dact=None,
-             act=None, dx_colsum=None):
+             act=None, dx_colsum=None, rows_dev=None):
     """y = x w^T + b.  dx[M,K] (+)= dy[M,N] @ w[N,K];  dw[N,K] += dy^T x;  db[N] += colsum(dy) (skipped when db is None:
     the producer of dy already accumulated it).  dact/act: dx is multiplied by act'(dact) in the GEMM epilogue, and
     dx_colsum receives the column sums of the result (bias gradient of the layer below)."""
     if dx is not None:
         if dact is not None or dx_colsum is not None:
             ops.gemm_fused(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec, dact=dact, act=act,
-                           colsum=dx_colsum)
+                           colsum=dx_colsum, rows_dev=rows_dev)
         else:
-            ops.gemm(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec)
-    ops.gemm(dy, x, dw, N, K, M, transA=True, lda=lddy or N, ldb=lda_x, accumulate=True, precision=prec)
+            ops.gemm(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec, rows_dev=rows_dev)
+    ops.gemm(dy, x, dw, N, K, M, transA=True, lda=lddy or N, ldb=lda_x, accumulate=True, precision=prec, rows_dev=rows_dev)
     if db is not None:
-        ops.colsum_accum(dy, M, N, db, ldx=lddy)
+        ops.colsum_accum(dy, M, N, db, ldx=lddy, rows_dev=rows_dev)
 
 
 # ==================================================================================================
@@ -169,7 +170,12 @@ def _lin_bwd(dy, M, N, x, K, w, dx, dw, db, lda_x=None, accumulate_dx=False, pre
 # registered on the tables' RowGrad.
 # ==================================================================================================
 class SASRecTower:
-    """unirec/model/sequential/sasrec.py:59-76 over modules.TransformerEncoder (modules.py:247-433)."""
+    """unirec/model/sequential/sasrec.py:59-76 over modules.TransformerEncoder (modules.py:247-433).
+
+    Token layout: the encoder runs on the LIVE positions only (csrc/pack.cu: real items + position L-1, every position of a
+    sequence without real items), packed sample by sample into the first n_tok rows of [B*L, .] buffers.  n_tok stays on the
+    device: launches are sized for B*L rows and every kernel stops at n_tok (`rows_dev`), so the step needs no host
+    synchronisation and remains CUDA-graph capturable.  `pack_sequences: 0` uses the identity map (all B*L positions)."""
 
     def __init__(self, eng, cfg):
         self.eng = eng
@@ -182,6 +188,7 @@ class SASRecTower:
         self.causal = bool(cfg['use_position_emb'])
         self.dh = self.d // self.H
         self.trim_last = bool(int(cfg.get('trim_last_layer', 1)))    # 0: compute the dead rows of the last layer too (A/B testing)
+        self.packed = bool(int(cfg.get('pack_sequences', 1)))        # 0: keep every position (identity token map)
         if float(cfg.get('hidden_dropout_prob', 0) or 0) > 0 or float(cfg.get('attn_dropout_prob', 0) or 0) > 0:
             raise ValueError('unirec_b200: dropout > 0 is not implemented in the fused encoder yet; set '
                              'hidden_dropout_prob=0 and attn_dropout_prob=0 (ignoring it silently would change training)')
@@ -201,162 +208,171 @@ class SASRecTower:
                       f + 'LayerNorm.weight', f + 'LayerNorm.bias']
         return names
 
+    def _names(self, i):
+        return 'trm_encoder.layer.%d.multi_head_attention.' % i, 'trm_encoder.layer.%d.feed_forward.' % i
+
+    def _pack(self, item_seq):
+        ws = self.eng.ws
+        B, L = item_seq.shape
+        pk = dict(offs=ws.get('pk_offs', (B + 1,), torch.int32), tok_src=ws.get('pk_src', (B * L,), torch.int32),
+                  tok_inv=ws.get('pk_inv', (B * L,), torch.int32), last=ws.get('pk_last', (B,), torch.int32),
+                  n=ws.get('pk_n', (1,), torch.int32))
+        ops.pack_tokens(item_seq, pk['offs'], pk['tok_src'], pk['tok_inv'], pk['last'], pk['n'], keep_all=not self.packed)
+        return pk
+
     # ---------------------------------------------------------------- forward
     def forward(self, item_seq, save=True, **_):
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
         B, L = item_seq.shape
         d, T = self.d, B * L
+        item_seq = item_seq.contiguous()
+        pk = self._pack(item_seq)
         table, index = eng.seq_rows_source(item_seq)
         self.seq_src = (table, index)
         pos = fp.p('position_embedding.weight') if self.causal else None
         x = ws.get('x0', (T, d))
         self.mean0, self.rstd0 = ws.get('mean0', (T,)), ws.get('rstd0', (T,))
         ops.seq_prep_ln_fwd(table, pos, fp.p('LayerNorm.weight'), fp.p('LayerNorm.bias'), self.eps, index, x,
-                            self.mean0, self.rstd0)
+                            self.mean0, self.rstd0, tok_src=pk['tok_src'], n_tok=pk['n'])
         self.saved = []
-        self.item_seq = item_seq
+        self.item_seq, self.pk = item_seq, pk
         user = ws.get('user_emb', (B, d))
         for i in range(self.n_layers):
             tag = str(i) if save else 'e'
             if i == self.n_layers - 1 and self.trim_last:
-                st = self._layer_fwd_last(i, x, item_seq, tag, user)
+                st = self._layer_fwd_last(i, x, item_seq, pk, tag, user)
             else:
-                st = self._layer_fwd_full(i, x, item_seq, tag)
+                st = self._layer_fwd_full(i, x, item_seq, pk, tag)
             if save:
                 self.saved.append(st)
             x = st[-1]
         if not self.trim_last:
-            user.copy_(x.view(B, L, d)[:, L - 1, :])
+            ops.gather_rows(x, pk['last'], out=user)
         return user
 
-    def _names(self, i):
-        return 'trm_encoder.layer.%d.multi_head_attention.' % i, 'trm_encoder.layer.%d.feed_forward.' % i
-
-    def _layer_fwd_full(self, i, x, item_seq, tag):
+    def _layer_fwd_full(self, i, x, item_seq, pk, tag):
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
         B, L = item_seq.shape
-        d, I, H, T, prec = self.d, self.I, self.H, B * L, eng.prec
+        d, I, H, T, prec, n = self.d, self.I, self.H, B * L, eng.prec, pk['n']
         a, f = self._names(i)
         wqkv, _ = fp.span(a + 'query.weight', a + 'value.weight')
         bqkv, _ = fp.span(a + 'query.bias', a + 'value.bias')
         qkv = ws.get('qkv' + tag, (T, 3 * d))
-        _lin_fwd(x, T, d, wqkv, bqkv, 3 * d, qkv, prec=prec)
+        ops.gemm(x, wqkv, qkv, T, 3 * d, d, transB=True, bias=bqkv, precision=prec, rows_dev=n)
         ctx, lse = ws.get('ctx' + tag, (T, d)), ws.get('lse' + tag, (B, H, L))
-        ops.attn_fwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse)
+        ops.attn_fwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, offs=pk['offs'], tok_src=pk['tok_src'])
         z1 = ws.get('z1' + tag, (T, d))
-        _lin_fwd(ctx, T, d, fp.p(a + 'dense.weight'), fp.p(a + 'dense.bias'), d, z1, prec=prec)
+        ops.gemm(ctx, fp.p(a + 'dense.weight'), z1, T, d, d, transB=True, bias=fp.p(a + 'dense.bias'), precision=prec, rows_dev=n)
         x1 = ws.get('x1' + tag, (T, d))
         m1, r1 = ws.get('m1' + tag, (T,)), ws.get('r1' + tag, (T,))
-        ops.add_ln_fwd(z1, x, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1)
+        ops.add_ln_fwd(z1, x, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1, rows_dev=n)
         hpre, hact = ws.get('hpre' + tag, (T, I)), ws.get('hact' + tag, (T, I))
-        _lin_fwd(x1, T, d, fp.p(f + 'dense_1.weight'), fp.p(f + 'dense_1.bias'), I, hact, act=self.act, preact=hpre,
-                 prec=prec)
+        ops.gemm(x1, fp.p(f + 'dense_1.weight'), hact, T, I, d, transB=True, bias=fp.p(f + 'dense_1.bias'), act=self.act,
+                 preact=hpre, precision=prec, rows_dev=n)
         z2 = ws.get('z2' + tag, (T, d))
-        _lin_fwd(hact, T, I, fp.p(f + 'dense_2.weight'), fp.p(f + 'dense_2.bias'), d, z2, prec=prec)
+        ops.gemm(hact, fp.p(f + 'dense_2.weight'), z2, T, d, I, transB=True, bias=fp.p(f + 'dense_2.bias'), precision=prec,
+                 rows_dev=n)
         x2 = ws.get('x2' + tag, (T, d))
         m2, r2 = ws.get('m2' + tag, (T,)), ws.get('r2' + tag, (T,))
-        ops.add_ln_fwd(z2, x1, fp.p(f + 'LayerNorm.weight'), fp.p(f + 'LayerNorm.bias'), self.eps, x2, m2, r2)
+        ops.add_ln_fwd(z2, x1, fp.p(f + 'LayerNorm.weight'), fp.p(f + 'LayerNorm.bias'), self.eps, x2, m2, r2, rows_dev=n)
         return ('full', x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, x2)
 
-    def _layer_fwd_last(self, i, x, item_seq, tag, user):
+    def _layer_fwd_last(self, i, x, item_seq, pk, tag, user):
         """Last encoder layer: only position L-1 of its output reaches the scorer (sasrec.py:74-75), so everything after the
-        key/value projection is computed for the B last rows only.  Keys and values still cover every position.  Results are
-        identical to the full computation: the other L-1 output rows are dead values in the reference."""
+        key/value projection is computed for the B last rows only (compact [B, .] buffers).  Keys and values still cover every
+        live position.  Results are identical to the full computation: the other output rows are dead values in the reference."""
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
         B, L = item_seq.shape
-        d, I, H, T, prec = self.d, self.I, self.H, B * L, eng.prec
+        d, I, H, T, prec, n = self.d, self.I, self.H, B * L, eng.prec, pk['n']
         a, f = self._names(i)
         wqkv, _ = fp.span(a + 'query.weight', a + 'value.weight')
         bqkv, _ = fp.span(a + 'query.bias', a + 'value.bias')
         qkv = ws.get('qkv' + tag, (T, 3 * d))
-        xl = x.view(B, L, d)[:, L - 1, :]                                  # [B, d], row stride L*d
-        # K | V for every position (rows d..3d of the packed weight), Q for the last position only
-        ops.gemm(x, wqkv[d * d:], qkv[:, d:], T, 2 * d, d, transB=True, ldc=3 * d, bias=bqkv[d:], precision=prec)
-        ops.gemm(xl, wqkv[:d * d], qkv.view(B, L, 3 * d)[:, L - 1, :], B, d, d, transB=True, lda=L * d, ldc=L * 3 * d,
-                 bias=bqkv[:d], precision=prec)
-        ctx, lse = ws.get('ctx' + tag, (T, d)), ws.get('lse' + tag, (B, H, L))
-        ops.attn_fwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, q_only_last=True)
-        ctxl = ctx.view(B, L, d)[:, L - 1, :]
+        # K | V for every live position (rows d..3d of the packed weight), Q for the last position only
+        ops.gemm(x, wqkv[d * d:], qkv[:, d:], T, 2 * d, d, transB=True, ldc=3 * d, bias=bqkv[d:], precision=prec, rows_dev=n)
+        xl = ops.gather_rows(x, pk['last'], out=ws.get('xl' + tag, (B, d)))
+        ql = ws.get('ql' + tag, (B, d))
+        ops.gemm(xl, wqkv[:d * d], ql, B, d, d, transB=True, bias=bqkv[:d], precision=prec)
+        ctx, lse = ws.get('ctxl' + tag, (B, d)), ws.get('lse' + tag, (B, H, L))
+        ops.attn_fwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, q_only_last=True, offs=pk['offs'],
+                     tok_src=pk['tok_src'], q_last=ql)
         z1 = ws.get('z1l' + tag, (B, d))
-        ops.gemm(ctxl, fp.p(a + 'dense.weight'), z1, B, d, d, transB=True, lda=L * d, bias=fp.p(a + 'dense.bias'),
-                 precision=prec)
+        ops.gemm(ctx, fp.p(a + 'dense.weight'), z1, B, d, d, transB=True, bias=fp.p(a + 'dense.bias'), precision=prec)
         x1 = ws.get('x1l' + tag, (B, d))
         m1, r1 = ws.get('m1l' + tag, (B,)), ws.get('r1l' + tag, (B,))
-        ops.add_ln_fwd(z1, xl, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1, rows=B, d=d,
-                       ldr=L * d)
+        ops.add_ln_fwd(z1, xl, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1, rows=B, d=d)
         hpre, hact = ws.get('hprel' + tag, (B, I)), ws.get('hactl' + tag, (B, I))
         _lin_fwd(x1, B, d, fp.p(f + 'dense_1.weight'), fp.p(f + 'dense_1.bias'), I, hact, act=self.act, preact=hpre, prec=prec)
         z2 = ws.get('z2l' + tag, (B, d))
         _lin_fwd(hact, B, I, fp.p(f + 'dense_2.weight'), fp.p(f + 'dense_2.bias'), d, z2, prec=prec)
         m2, r2 = ws.get('m2l' + tag, (B,)), ws.get('r2l' + tag, (B,))
         ops.add_ln_fwd(z2, x1, fp.p(f + 'LayerNorm.weight'), fp.p(f + 'LayerNorm.bias'), self.eps, user, m2, r2, rows=B, d=d)
-        return ('last', x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, user)
+        return ('last', x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, xl, ql, user)
 
     # ---------------------------------------------------------------- backward
     def backward(self, d_user):
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
-        item_seq = self.item_seq
+        item_seq, pk = self.item_seq, self.pk
         B, L = item_seq.shape
         d, T = self.d, B * L
         dx = None
         for i in reversed(range(self.n_layers)):
             st = self.saved[i]
             if st[0] == 'last':
-                dx = self._layer_bwd_last(i, st, d_user, item_seq)
+                dx = self._layer_bwd_last(i, st, d_user, item_seq, pk)
             else:
                 if dx is None:                      # untrimmed last layer: the loss gradient enters at position L-1
                     dx = ws.get('dx_a', (T, d), zero=True)
-                    dx.view(B, L, d)[:, L - 1, :] = d_user
-                dx = self._layer_bwd_full(i, st, dx, item_seq)
+                    ops.scatter_add_rows(dx, pk['last'], d_user, pad_id=-1)
+                dx = self._layer_bwd_full(i, st, dx, item_seq, pk)
         table, index = self.seq_src
         pos = fp.p('position_embedding.weight') if self.causal else None
         drows = ws.get('drows', (T, d))
         ops.seq_prep_ln_bwd(table, pos, fp.p('LayerNorm.weight'), index, self.mean0, self.rstd0, dx, drows,
                             fp.g('LayerNorm.weight'), fp.g('LayerNorm.bias'),
-                            fp.g('position_embedding.weight') if self.causal else None)
+                            fp.g('position_embedding.weight') if self.causal else None, tok_inv=pk['tok_inv'])
         eng.add_seq_rowgrad(item_seq, drows)
 
-    def _layer_bwd_full(self, i, st, dx, item_seq):
+    def _layer_bwd_full(self, i, st, dx, item_seq, pk):
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
         B, L = item_seq.shape
-        d, I, H, T, prec = self.d, self.I, self.H, B * L, eng.prec
+        d, I, H, T, prec, n = self.d, self.I, self.H, B * L, eng.prec, pk['n']
         a, f = self._names(i)
         _, x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, _x2 = st
-        # x2 = LN(z2), z2 = ffn(x1) + x1.  Bias gradients ride on the kernels that produce the corresponding dy.
+        # x2 = LN(z2), z2 = ffn(x1) + x1.  Bias gradients ride on the kernels that produce the corresponding dy.  Every
+        # token-reduction GEMM (dW = dy^T x) has one operand written by an LN kernel, whose rows [n_tok, roundup32) are zero.
         dz2 = ws.get('dz2', (T, d))
         ops.add_ln_bwd(z2, fp.p(f + 'LayerNorm.weight'), m2, r2, dx, dz2, fp.g(f + 'LayerNorm.weight'),
-                       fp.g(f + 'LayerNorm.bias'), dzsum=fp.g(f + 'dense_2.bias'))
+                       fp.g(f + 'LayerNorm.bias'), dzsum=fp.g(f + 'dense_2.bias'), rows_dev=n)
         dh = ws.get('dh', (T, I))
         # dh = (dz2 @ W2) * act'(hpre), db1 += colsum(dh): one GEMM with a fused epilogue
         _lin_bwd(dz2, T, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'), None, prec=prec,
-                 dact=hpre, act=self.act, dx_colsum=fp.g(f + 'dense_1.bias'))
+                 dact=hpre, act=self.act, dx_colsum=fp.g(f + 'dense_1.bias'), rows_dev=n)
         # dx1 = dz2 (residual) + dh @ W1   -> accumulate into dz2
         _lin_bwd(dh, T, I, x1, d, fp.p(f + 'dense_1.weight'), dz2, fp.g(f + 'dense_1.weight'), None,
-                 accumulate_dx=True, prec=prec)
+                 accumulate_dx=True, prec=prec, rows_dev=n)
         # x1 = LN(z1), z1 = attn_out + x
         dz1 = ws.get('dz1_%d' % (i % 2), (T, d))     # becomes this layer's input gradient (no copy)
         ops.add_ln_bwd(z1, fp.p(a + 'LayerNorm.weight'), m1, r1, dz2, dz1, fp.g(a + 'LayerNorm.weight'),
-                       fp.g(a + 'LayerNorm.bias'), dzsum=fp.g(a + 'dense.bias'))
+                       fp.g(a + 'LayerNorm.bias'), dzsum=fp.g(a + 'dense.bias'), rows_dev=n)
         dctx = ws.get('dctx', (T, d))
-        _lin_bwd(dz1, T, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec)
+        _lin_bwd(dz1, T, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec, rows_dev=n)
         dqkv = ws.get('dqkv', (T, 3 * d))
-        ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv)
+        ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv, offs=pk['offs'], tok_src=pk['tok_src'])
         wqkv, gwqkv = fp.span(a + 'query.weight', a + 'value.weight')
         _, gbqkv = fp.span(a + 'query.bias', a + 'value.bias')
         # dx = dz1 (residual) + dqkv @ Wqkv  -> accumulate into dz1
-        _lin_bwd(dqkv, T, 3 * d, x, d, wqkv, dz1, gwqkv, gbqkv, accumulate_dx=True, prec=prec)
+        _lin_bwd(dqkv, T, 3 * d, x, d, wqkv, dz1, gwqkv, gbqkv, accumulate_dx=True, prec=prec, rows_dev=n)
         return dz1
 
-    def _layer_bwd_last(self, i, st, d_user, item_seq):
+    def _layer_bwd_last(self, i, st, d_user, item_seq, pk):
         """Backward of _layer_fwd_last: the loss gradient exists at position L-1 only, so everything down to the attention is
-        B rows; dK/dV (all positions) and dQ (last position) then give the full-size input gradient."""
+        B rows; dK/dV (all live positions) and dQ (last position) then give the full-size input gradient."""
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
         B, L = item_seq.shape
-        d, I, H, T, prec = self.d, self.I, self.H, B * L, eng.prec
+        d, I, H, T, prec, n = self.d, self.I, self.H, B * L, eng.prec, pk['n']
         a, f = self._names(i)
-        _, x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, _user = st
-        xl = x.view(B, L, d)[:, L - 1, :]
-        ctxl = ctx.view(B, L, d)[:, L - 1, :]
+        _, x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, xl, ql, _user = st
         dz2 = ws.get('dz2l', (B, d))
         ops.add_ln_bwd(z2, fp.p(f + 'LayerNorm.weight'), m2, r2, d_user, dz2, fp.g(f + 'LayerNorm.weight'),
                        fp.g(f + 'LayerNorm.bias'), rows=B, d=d, dzsum=fp.g(f + 'dense_2.bias'))
@@ -368,29 +384,25 @@ class SASRecTower:
         dz1 = ws.get('dz1l', (B, d))
         ops.add_ln_bwd(z1, fp.p(a + 'LayerNorm.weight'), m1, r1, dz2, dz1, fp.g(a + 'LayerNorm.weight'),
                        fp.g(a + 'LayerNorm.bias'), rows=B, d=d, dzsum=fp.g(a + 'dense.bias'))
-        # dctx (last rows of a [T, d] buffer, the layout attn_bwd reads) = dz1 @ Wo ; dWo += dz1^T ctx_last
-        dctx = ws.get('dctx', (T, d))
-        dctxl = dctx.view(B, L, d)[:, L - 1, :]
-        ops.gemm(dz1, fp.p(a + 'dense.weight'), dctxl, B, d, d, ldc=L * d, precision=prec)
-        ops.gemm(dz1, ctxl, fp.g(a + 'dense.weight'), d, d, B, transA=True, lda=d, ldb=L * d, accumulate=True, precision=prec)
-        dqkv = ws.get('dqkv', (T, 3 * d))
-        ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv, q_only_last=True)
-        dql = dqkv.view(B, L, 3 * d)[:, L - 1, :d]                          # [B, d], row stride L*3d
+        dctx = ws.get('dctxl', (B, d))
+        _lin_bwd(dz1, B, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec)
+        dqkv, dql = ws.get('dqkv', (T, 3 * d)), ws.get('dql', (B, d))
+        ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv, q_only_last=True, offs=pk['offs'],
+                     tok_src=pk['tok_src'], q_last=ql, dq_last=dql)
         dkv = dqkv[:, d:]                                                  # [T, 2d], row stride 3d
         wqkv, gwqkv = fp.span(a + 'query.weight', a + 'value.weight')
         _, gbqkv = fp.span(a + 'query.bias', a + 'value.bias')
         wq, wkv, gwq, gwkv = wqkv[:d * d], wqkv[d * d:], gwqkv[:d * d], gwqkv[d * d:]
-        # input gradient: every row gets dKV @ Wkv; the last rows add dQ @ Wq and the residual branch (dz1)
+        # input gradient: every live row gets dKV @ Wkv; the last rows add dQ @ Wq and the residual branch (dz1)
         dxf = ws.get('dz1_%d' % (i % 2), (T, d))
-        ops.gemm(dkv, wkv, dxf, T, d, 2 * d, lda=3 * d, precision=prec)
-        dxl = dxf.view(B, L, d)[:, L - 1, :]
-        ops.gemm(dql, wq, dxl, B, d, d, lda=L * 3 * d, ldc=L * d, accumulate=True, precision=prec)
-        dxl += dz1
-        # weight / bias gradients of the projections
-        ops.gemm(dkv, x, gwkv, 2 * d, d, T, transA=True, lda=3 * d, ldb=d, accumulate=True, precision=prec)
-        ops.gemm(dql, xl, gwq, d, d, B, transA=True, lda=L * 3 * d, ldb=L * d, accumulate=True, precision=prec)
-        ops.colsum_accum(dkv, T, 2 * d, gbqkv[d:], ldx=3 * d)
-        ops.colsum_accum(dql, B, d, gbqkv[:d], ldx=L * 3 * d)
+        ops.gemm(dkv, wkv, dxf, T, d, 2 * d, lda=3 * d, precision=prec, rows_dev=n)
+        ops.gemm(dql, wq, dz1, B, d, d, accumulate=True, precision=prec)        # dz1 <- dz1 + dQ @ Wq
+        ops.scatter_add_rows(dxf, pk['last'], dz1, pad_id=-1)
+        # weight / bias gradients of the projections (x comes from an LN kernel: zero rows up to the next k-block)
+        ops.gemm(dkv, x, gwkv, 2 * d, d, T, transA=True, lda=3 * d, ldb=d, accumulate=True, precision=prec, rows_dev=n)
+        ops.gemm(dql, xl, gwq, d, d, B, transA=True, lda=d, ldb=d, accumulate=True, precision=prec)
+        ops.colsum_accum(dkv, T, 2 * d, gbqkv[d:], ldx=3 * d, rows_dev=n)
+        ops.colsum_accum(dql, B, d, gbqkv[:d])
         return dxf
 
 

@@ -102,41 +102,62 @@ def pool_sum_fwd(table, item_seq, item_seq_len, alpha, user_table=None, user_id=
 
 
 # ------------------------------------------------------------------ layer norm family
-def seq_prep_ln_fwd(table, pos, gamma, beta, eps, item_seq, Y, mean, rstd):
+def _i32(t):
+    return _ptr(t, torch.int32) if t is not None else None
+
+
+def seq_prep_ln_fwd(table, pos, gamma, beta, eps, item_seq, Y, mean, rstd, tok_src=None, n_tok=None):
     B, L = item_seq.shape
     _call('ur_seq_prep_ln_fwd_f32', _f32(table), _f32(pos), _f32(gamma), _f32(beta), float(eps),
-          _ptr(item_seq, torch.int32), B, L, table.shape[1], _f32(Y), _f32(mean), _f32(rstd), _stream())
+          _ptr(item_seq, torch.int32), B, L, table.shape[1], _f32(Y), _f32(mean), _f32(rstd), _i32(tok_src), _i32(n_tok),
+          _stream())
     return Y
 
 
-def seq_prep_ln_bwd(table, pos, gamma, item_seq, mean, rstd, dY, dX, dgamma, dbeta, dpos):
+def seq_prep_ln_bwd(table, pos, gamma, item_seq, mean, rstd, dY, dX, dgamma, dbeta, dpos, tok_inv=None):
     B, L = item_seq.shape
     _call('ur_seq_prep_ln_bwd_f32', _f32(table), _f32(pos), _f32(gamma), _ptr(item_seq, torch.int32), B, L,
-          table.shape[1], _f32(mean), _f32(rstd), _f32(dY), _f32(dX), _f32(dgamma), _f32(dbeta), _f32(dpos), _stream())
+          table.shape[1], _f32(mean), _f32(rstd), _f32(dY), _f32(dX), _f32(dgamma), _f32(dbeta), _f32(dpos), _i32(tok_inv),
+          _stream())
     return dX
 
 
-def add_ln_fwd(X, R, gamma, beta, eps, Y, mean, rstd, rows=None, d=None, ldx=None, ldr=None, ldy=None):
+def pack_tokens(item_seq, offs, tok_src, tok_inv, last_tok, n_tok, keep_all=False):
+    """Live-token map of a left-padded [B, L] id matrix (csrc/pack.cu)."""
+    B, L = item_seq.shape
+    _call('ur_pack_tokens', _ptr(item_seq, torch.int32), B, L, int(keep_all), _i32(offs), _i32(tok_src), _i32(tok_inv),
+          _i32(last_tok), _i32(n_tok), _stream())
+
+
+def zero_tail_rows(X, n_dev, width=None, ld=None):
+    _call('ur_zero_tail_rows_f32', _f32(X), ld or X.shape[-1], width or X.shape[-1], _i32(n_dev), X.shape[0], _stream())
+
+
+def add_ln_fwd(X, R, gamma, beta, eps, Y, mean, rstd, rows=None, d=None, ldx=None, ldr=None, ldy=None, rows_dev=None):
     d = d or X.shape[-1]
     rows = rows if rows is not None else X.numel() // d
     _call('ur_add_ln_fwd_f32', _f32(X), ldx or d, _f32(R), ldr or d, _f32(gamma), _f32(beta), float(eps), rows, d,
-          _f32(Y), ldy or d, _f32(mean), _f32(rstd), _stream())
+          _f32(Y), ldy or d, _f32(mean), _f32(rstd), _i32(rows_dev), _stream())
     return Y
 
 
 def add_ln_bwd(Z, gamma, mean, rstd, dY, dZ, dgamma, dbeta, dExtra=None, rows=None, d=None, ldz=None, lddy=None,
-               ldde=None, lddz=None, dzsum=None):
+               ldde=None, lddz=None, dzsum=None, rows_dev=None):
     d = d or Z.shape[-1]
     rows = rows if rows is not None else Z.numel() // d
     _call('ur_add_ln_bwd_f32', _f32(Z), ldz or d, _f32(gamma), _f32(mean), _f32(rstd), _f32(dY), lddy or d,
-          _f32(dExtra), ldde or d, rows, d, _f32(dZ), lddz or d, _f32(dgamma), _f32(dbeta), _f32(dzsum), _stream())
+          _f32(dExtra), ldde or d, rows, d, _f32(dZ), lddz or d, _f32(dgamma), _f32(dbeta), _f32(dzsum), _i32(rows_dev), _stream())
     return dZ
 
 
 # ------------------------------------------------------------------ GEMM
 def gemm(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, act=None,
-         preact=None, ldp=None, accumulate=False, precision=0):
-    """C[M,N] (+)= act(op(A)[M,K] @ op(B)[K,N] + bias).  Row-major; default leading dims = stored row length."""
+         preact=None, ldp=None, accumulate=False, precision=0, rows_dev=None):
+    """C[M,N] (+)= act(op(A)[M,K] @ op(B)[K,N] + bias).  Row-major; default leading dims = stored row length.
+    rows_dev: device int32 live token count -- bounds M (row-parallel products) or K (transA: reductions over tokens)."""
+    if rows_dev is not None:
+        return gemm_fused(A, B, C, M, N, K, transA=transA, transB=transB, lda=lda, ldb=ldb, ldc=ldc, bias=bias, act=act,
+                          preact=preact, ldp=ldp, accumulate=accumulate, precision=precision, rows_dev=rows_dev)
     if lda is None:
         lda = M if transA else K
     if ldb is None:
@@ -149,7 +170,7 @@ def gemm(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None, ldc=N
 
 
 def gemm_fused(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, act=None,
-               preact=None, ldp=None, accumulate=False, precision=0, dact=None, ldd=None, colsum=None):
+               preact=None, ldp=None, accumulate=False, precision=0, dact=None, ldd=None, colsum=None, rows_dev=None):
     """gemm() plus two fused epilogue stages: C = (A @ B) * act'(dact) (activation backward) and colsum += column sums of C."""
     if lda is None:
         lda = M if transA else K
@@ -158,7 +179,8 @@ def gemm_fused(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None,
     if ldc is None:
         ldc = N
     _call('ur_gemm_fused_f32', int(transA), int(transB), M, N, K, _f32(A), lda, _f32(B), ldb, _f32(C), ldc, _f32(bias),
-          ACT_CODES[act], _f32(preact), ldp or N, int(accumulate), int(precision), _f32(dact), ldd or N, _f32(colsum), _stream())
+          ACT_CODES[act], _f32(preact), ldp or N, int(accumulate), int(precision), _f32(dact), ldd or N, _f32(colsum),
+          _i32(rows_dev), (2 if transA else 1) if rows_dev is not None else 0, _stream())
     return C
 
 
@@ -174,23 +196,24 @@ def act_bwd(dY, preact, act):
     return dY
 
 
-def colsum_accum(X, M, N, out, ldx=None):
-    _call('ur_colsum_accum_f32', _f32(X), ldx or N, M, N, _f32(out), _stream())
+def colsum_accum(X, M, N, out, ldx=None, rows_dev=None):
+    _call('ur_colsum_accum_f32', _f32(X), ldx or N, M, N, _f32(out), _i32(rows_dev), _stream())
     return out
 
 
 # ------------------------------------------------------------------ attention
-def attn_fwd(qkv, item_seq, H, dh, causal, ctx, lse, q_only_last=False):
+def attn_fwd(qkv, item_seq, H, dh, causal, ctx, lse, q_only_last=False, offs=None, tok_src=None, q_last=None):
     B, L = item_seq.shape
     _call('ur_attn_fwd_f32', _f32(qkv), _ptr(item_seq, torch.int32), B, L, H, dh, int(causal), int(q_only_last),
-          _f32(ctx), _f32(lse), _stream())
+          _f32(ctx), _f32(lse), _i32(offs), _i32(tok_src), _f32(q_last), _stream())
     return ctx
 
 
-def attn_bwd(qkv, item_seq, H, dh, causal, ctx, lse, dctx, dqkv, q_only_last=False):
+def attn_bwd(qkv, item_seq, H, dh, causal, ctx, lse, dctx, dqkv, q_only_last=False, offs=None, tok_src=None, q_last=None,
+             dq_last=None):
     B, L = item_seq.shape
     _call('ur_attn_bwd_f32', _f32(qkv), _ptr(item_seq, torch.int32), B, L, H, dh, int(causal), int(q_only_last),
-          _f32(ctx), _f32(lse), _f32(dctx), _f32(dqkv), _stream())
+          _f32(ctx), _f32(lse), _f32(dctx), _f32(dqkv), _i32(offs), _i32(tok_src), _f32(q_last), _f32(dq_last), _stream())
     return dqkv
 
 
