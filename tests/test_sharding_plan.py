@@ -52,3 +52,40 @@ def test_partial_softmax_protocol_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, 29711, out), nprocs=2, join=True)
     assert len(out) == 2 and max(out.values()) < 1e-5, dict(out)
+
+
+def _ckpt_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from types import SimpleNamespace
+    g = torch.Generator().manual_seed(5)
+    V, d = 1003, 8                       # not a multiple of the world size: ranks hold different row counts
+    full = torch.randn(V, d, generator=g)
+    local = sharding.shard_table(full, world, rank)
+
+    class M(SimpleNamespace):
+        def state_dict(self):
+            return {'item_embedding.weight': local, 'LayerNorm.weight': torch.ones(d)}
+    m = M(shard_world=world, shard_rank=rank, n_items=V)
+    sd = sharding.full_state_dict(m)
+    ok = True
+    if rank == 0:
+        ok = torch.equal(sd['item_embedding.weight'], full) and torch.equal(sd['LayerNorm.weight'], torch.ones(d))
+    # gather in small chunks too (several send/recv rounds per rank)
+    again = sharding.gather_full_table(local, V, world, rank, chunk_rows=100)
+    if rank == 0:
+        ok = ok and torch.equal(again, full)
+    # loading a full (reference-style) checkpoint cuts it back to the local rows; local shards pass through
+    back = sharding.localize_state_dict(m, {'item_embedding.weight': full, 'LayerNorm.weight': torch.ones(d)})
+    ok = ok and torch.equal(back['item_embedding.weight'], local)
+    ok = ok and torch.equal(sharding.localize_state_dict(m, {'item_embedding.weight': local})['item_embedding.weight'], local)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_checkpoint_gather_and_localize_gloo_world2():
+    """§8 f4: checkpoints of row-sharded models hold full tables (reference-compatible) and load back into shards."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ckpt_worker, args=(2, 29713, out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}, dict(out)

@@ -87,11 +87,17 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
     float sq = 0.f;
     const bool is_adam = (mode == OPT_ADAM || mode == OPT_ADAMW);
     const bool update = (mode != OPT_SQNORM) && !skip;
-    for (int64_t u = ub + group0; u < nu; u += ngroups) {
-        const int64_t id = uniq[u];
-        int32_t e = head[id];
+    // (row id, list head) of the NEXT row are fetched one iteration ahead: the chain uniq -> head (a random 4-byte read of a
+    // 40 MB array) is ~1.3 us of the ~2.3 us dependent chain per row, so taking it off the critical path lets the same number
+    // of resident warps keep nearly twice as many row loads in flight.
+    int64_t u = ub + group0;
+    int64_t id = u < nu ? (int64_t)__ldg(uniq + u) : -1;
+    int32_t e = u < nu ? head[id] : -1;
+    for (; u < nu; u += ngroups) {
+        const int64_t u_next = u + ngroups;
+        const int64_t id_next = u_next < nu ? (int64_t)__ldg(uniq + u_next) : -1;
         // Issue the parameter / moment loads FIRST: they do not depend on the list walk, so their HBM latency overlaps
-        // the dependent chain head -> entry -> source row below.
+        // the dependent chain entry -> source row below.
         float4 P[VPL], M[VPL], W[VPL];
         if (update) {
 #pragma unroll
@@ -101,6 +107,7 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
                 if (is_adam) { M[v] = ld_stream_rw(mom + o); W[v] = ld_stream_rw(var + o); }
             }
         }
+        const int32_t e_next = id_next >= 0 ? head[id_next] : -1;       // distinct row: not the head reset below
         float4 g[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -118,10 +125,11 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
         if (mode == OPT_SQNORM) {
 #pragma unroll
             for (int v = 0; v < VPL; ++v) sq += f4_dot(g[v], g[v]);
+            id = id_next; e = e_next;
             continue;
         }
         if (col == 0) head[id] = -1;
-        if (skip) continue;
+        if (skip) { id = id_next; e = e_next; continue; }
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             const int64_t o = id * D4 + v * LPR + col;
@@ -145,6 +153,7 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
                 stg_stream(mom + o, m); stg_stream(var + o, w); stg_stream(table + o, p);
             }
         }
+        id = id_next; e = e_next;
     }
     if (mode == OPT_SQNORM) {
         sq = warp_sum(sq);

@@ -284,7 +284,11 @@ class Trainer(object):
         checkpoint_file = filename if filename else self.saved_model_file
         checkpoint = torch.load(checkpoint_file, map_location=self.accelerator.device, weights_only=False)
         model = self.accelerator.unwrap_model(self.model)
-        model.load_state_dict(checkpoint['state_dict'], strict=False)
+        sd = checkpoint['state_dict']
+        if int(getattr(model, 'shard_world', 1)) > 1:        # full tables in the file -> this rank's rows
+            from unirec_b200.sharding import localize_state_dict
+            sd = localize_state_dict(model, sd)
+        model.load_state_dict(sd, strict=False)
         self.logger.info('Loading model from {0}. The best epoch was {1}'.format(checkpoint_file, checkpoint['cur_epoch']))
         if self.config.get('freeze', 0):
             for name, param in model.named_parameters():
@@ -292,13 +296,21 @@ class Trainer(object):
                     param.requires_grad = False
 
     def save_model(self, filename, optimizer, scheduler, cur_epoch=-1, cur_step=-1, best_valid_score=None, config=None):
-        """Same checkpoint dict as the reference (trainer.py:389-398)."""
+        """Same checkpoint dict as the reference (trainer.py:389-398).  Row-sharded tables are re-assembled on rank 0 first
+        (collective: every rank must call save_model), so the file holds full [n_items, d] tables like a reference checkpoint.
+        Optimizer moments of sharded tables stay per-rank (saved by rank 0 for its shard only)."""
+        model = self.accelerator.unwrap_model(self.model)
+        if int(getattr(model, 'shard_world', 1)) > 1:
+            from unirec_b200.sharding import full_state_dict
+            model_sd = full_state_dict(model)
+        else:
+            model_sd = model.state_dict()
         state = {
             'config': config,
             'cur_epoch': cur_epoch,
             'cur_step': cur_step,
             'best_valid_score': best_valid_score,
-            'state_dict': self.accelerator.unwrap_model(self.model).state_dict(),
+            'state_dict': model_sd,
             'optimizer': optimizer.optimizer.state_dict() if optimizer is not None else None,
             'scheduler': scheduler.state_dict() if scheduler is not None else None,
         }

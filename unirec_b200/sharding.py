@@ -53,6 +53,61 @@ def unshard_tables(shards):
     return out
 
 
+SHARDED_TABLES = ('item_embedding.weight',)       # parameters stored row-sharded when table_shard_world > 1
+
+
+def gather_full_table(local, n_rows, world, rank, group=None, chunk_rows=1 << 20):
+    """Re-assemble a row-sharded [n_rows, d] table on rank 0 (host memory) for a reference-compatible checkpoint
+    (§8 f4; reference dict: unirec/facility/trainer.py:389-398).  Shards travel in chunks of `chunk_rows` rows, so the
+    device-side staging stays small next to a 10M-row table.  Returns the full CPU tensor on rank 0, None elsewhere."""
+    d = local.shape[1]
+    full = torch.empty(n_rows, d, dtype=local.dtype) if rank == 0 else None
+    for src in range(world):
+        rows = local_rows_count(n_rows, world, src)
+        for c0 in range(0, rows, chunk_rows):
+            c1 = min(rows, c0 + chunk_rows)
+            if src == 0:
+                if rank == 0:
+                    full[c0 * world:(c1 - 1) * world + 1:world] = local[c0:c1].detach().cpu()
+                continue
+            if rank == src:
+                dist.send(local[c0:c1].detach().contiguous(), dst=0, group=group)
+            elif rank == 0:
+                buf = torch.empty(c1 - c0, d, dtype=local.dtype, device=local.device)
+                dist.recv(buf, src=src, group=group)
+                full[src + c0 * world:src + (c1 - 1) * world + 1:world] = buf.cpu()
+    return full
+
+
+def full_state_dict(model, group=None):
+    """state_dict with every sharded table re-assembled (rank 0; other ranks get their local view back)."""
+    sd = model.state_dict()
+    W, r = int(getattr(model, 'shard_world', 1)), int(getattr(model, 'shard_rank', 0))
+    if W <= 1:
+        return sd
+    out = dict(sd)
+    for name in SHARDED_TABLES:
+        if name in sd:
+            full = gather_full_table(sd[name], int(model.n_items), W, r, group)
+            if r == 0:
+                out[name] = full
+    return out
+
+
+def localize_state_dict(model, state_dict):
+    """Inverse for loading: a full [n_items, d] table in `state_dict` (a reference checkpoint, or one written by
+    full_state_dict) is cut down to this rank's rows; already-local shards pass through."""
+    W, r = int(getattr(model, 'shard_world', 1)), int(getattr(model, 'shard_rank', 0))
+    if W <= 1:
+        return state_dict
+    out = dict(state_dict)
+    for name in SHARDED_TABLES:
+        t = out.get(name)
+        if t is not None and t.shape[0] == int(model.n_items) and t.shape[0] != local_rows_count(int(model.n_items), W, r):
+            out[name] = shard_table(t, W, r)
+    return out
+
+
 class ShardedEngine(Engine):
     """Engine whose embedding tables are row-sharded over `dist` ranks.  Softmax loss with SASRec / GRU towers (the
     north-star multi-GPU configuration); other combinations raise."""
