@@ -133,6 +133,7 @@ def main():
     ap.add_argument('--gemm-precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='keep Trainer.train_step eager (ncu launch lists)')
+    ap.add_argument('--shard-p2p', type=int, default=1, help='row-sharded tables: 1 = peer-memory reads over NVLink, 0 = NCCL exchange')
     ap.add_argument('--overlap', type=int, default=0, help='overlap_table_update mode (0 off, 1 early link, 2 + early update)')
     args = ap.parse_args()
     sys.argv = sys.argv[:1]
@@ -160,7 +161,7 @@ def main():
     cfg_args.update({k: v for k, v in w.items() if k not in ('K', 'B')})
     cfg_args.update(batch_size=B, n_sample_neg_train=K, gemm_precision=args.gemm_precision, epochs=1,
                     output_path=os.path.join(ROOT, 'gpurun_out', 'bench_ckpt'), table_shard_world=world,
-                    overlap_table_update=args.overlap, cuda_graph=0 if args.no_graph else 1)
+                    overlap_table_update=args.overlap, cuda_graph=0 if args.no_graph else 1, shard_p2p=args.shard_p2p)
     cfg = argument_parser.parse_arguments(cfg_args, argv=[])
     cfg['device'] = dev
     general.init_seed(2022)

@@ -50,11 +50,13 @@ int ur_pool_sum_fwd_f32(const float* table, int d, const int32_t* item_seq, int6
  * replaces: SASRec.forward_user_emb prologue, unirec/model/sequential/sasrec.py:60-69 */
 int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos /*nullable*/, const float* gamma, const float* beta, float eps,
                            const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd,
-                           const int32_t* tok_src /*nullable*/, const int32_t* n_tok_dev /*nullable*/, void* stream);
+                           const int32_t* tok_src /*nullable*/, const int32_t* n_tok_dev /*nullable*/,
+                           const void* shard_ptrs /*nullable: W peer pointers (int64) to the row shards*/, int shard_world, void* stream);
 /* dX[B*L,d] = gradient wrt the gathered rows (feeds the row-sparse table update); dgamma/dbeta/dpos are ACCUMULATED */
 int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* gamma, const int32_t* item_seq, int64_t B, int L,
                            int d, const float* mean, const float* rstd, const float* dY, float* dX, float* dgamma, float* dbeta,
-                           float* dpos /*nullable*/, const int32_t* tok_inv /*nullable*/, void* stream);
+                           float* dpos /*nullable*/, const int32_t* tok_inv /*nullable*/, const void* shard_ptrs /*nullable*/,
+                           int shard_world, void* stream);
 
 /* ---- K6: post-LN residual.  X <- X + R (kept for backward), Y = LayerNorm(X).
  * replaces: LayerNorm(hidden + input) unirec/model/modules.py:314, :353 */
@@ -159,7 +161,13 @@ int ur_rowlist_apply_f32(float* table, float* mom, float* var, int d, int32_t* h
                          int64_t coef1_group, int mode, float lr, float beta1, float beta2, float eps, float weight_decay,
                          const int32_t* step_dev, const float* grad_scale_dev, const int32_t* skip_flag, float* sqnorm_out,
                          const int32_t* u_begin_dev /*nullable*/, const int32_t* u_end_dev /*nullable*/, int small_ctas,
-                         void* stream);
+                         const void* src1_part_ptrs /*nullable: peer pointers, source 1 rows live in per-rank buffers*/,
+                         int64_t src1_part_rows, void* stream);
+
+/* ---- peer memory for the row-sharded tables (csrc/p2p.cu): CUDA IPC export / open of device buffers between the per-GPU processes of
+ * one box.  replaces: the reference's DDP all-reduce of dense table gradients (trainer.py:67,346) -- rows are read over NVLink instead. */
+int ur_ipc_export(const void* dev_ptr, void* handle_out /*64 host bytes*/, int64_t* offset_out /*host*/);
+int ur_ipc_open(const void* handle /*64 host bytes*/, int64_t offset, int64_t* ptr_out /*host*/);
 int ur_dense_opt_f32(float* param, const float* grad, float* mom, float* var, int64_t n, int mode, float lr, float beta1,
                      float beta2, float eps, float weight_decay, const int32_t* step_dev, const float* grad_scale_dev,
                      const int32_t* skip_flag, void* stream);

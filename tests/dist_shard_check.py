@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
-def main(name='sasrec_softmax'):
+def main(name='sasrec_softmax', p2p='1'):
     sys.argv = sys.argv[:1]
     from golden_util import Golden, rel_err
     from oracle import unirec_oracle as O
@@ -33,7 +33,8 @@ def main(name='sasrec_softmax'):
     B = g.batch['item_id'].shape[0]
     assert B % W == 0, (B, W)
     args = dict(g.cfg)
-    args.update(exp_name='shard', dataset='example', table_shard_world=W, table_shard_rank=r, table_shard_force=True)
+    args.update(exp_name='shard', dataset='example', table_shard_world=W, table_shard_rank=r, table_shard_force=True,
+                shard_p2p=int(p2p))
     cfg = argument_parser.parse_arguments(args, argv=[])
     cfg['device'] = dev
     general.init_seed(2022)
@@ -74,7 +75,7 @@ def main(name='sasrec_softmax'):
         worst = max(worst, rel_err(v.cpu(), p[k]))
     assert worst < 2e-3, worst
     if r == 0:
-        print('SHARD_OK world=%d loss=%.6f ref=%.6f max_rel_err=%.2e' % (W, float(loss), float(g.loss), worst))
+        print('SHARD_OK world=%d p2p=%d loss=%.6f ref=%.6f max_rel_err=%.2e' % (W, int(model._engine.p2p), float(loss), float(g.loss), worst))
     dist.barrier()
     dist.destroy_process_group()
 

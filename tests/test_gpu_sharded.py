@@ -10,13 +10,15 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(world, name):
+def _run(world, name, p2p=1):
     env = dict(os.environ)
     env.pop('RANK', None)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr',
-           '127.0.0.1', '--master-port', str(29600 + world), os.path.join(HERE, 'dist_shard_check.py'), name]
+           '127.0.0.1', '--master-port', str(29600 + world), os.path.join(HERE, 'dist_shard_check.py'), name, str(p2p)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0 and 'SHARD_OK' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    if world > 1 and not name.startswith('gru'):
+        assert ('p2p=%d' % p2p) in res.stdout, res.stdout[-500:]
 
 
 @pytest.mark.parametrize('name', ['sasrec_softmax', 'sasrec_softmax_d128', 'gru_softmax_h32'])
@@ -24,8 +26,10 @@ def test_sharded_engine_world1(name):
     _run(1, name)
 
 
-@pytest.mark.parametrize('name', ['sasrec_softmax', 'sasrec_softmax_d128'])
-def test_sharded_engine_world2(name):
+@pytest.mark.parametrize('name,p2p', [('sasrec_softmax', 1), ('sasrec_softmax_d128', 1), ('sasrec_softmax', 0)])
+def test_sharded_engine_world2(name, p2p):
+    """p2p=1: history rows / their gradients are read over NVLink through CUDA IPC mappings; p2p=0: NCCL reduce-scatter /
+    all-gather of [W, B*L, d] buffers.  Both must reproduce the single-GPU golden step."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
-    _run(2, name)
+    _run(2, name, p2p)

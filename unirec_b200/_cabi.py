@@ -18,8 +18,8 @@ SIGNATURES = {
     'ur_gather_rows_f32': 'plipilpp',
     'ur_scatter_add_rows_f32': 'plipilplpllp',
     'ur_pool_sum_fwd_f32': 'piplipfppppp',
-    'ur_seq_prep_ln_fwd_f32': 'ppppfpliippp' + 'pp' + 'p',
-    'ur_seq_prep_ln_bwd_f32': 'pppplii' + 'ppp' + 'pppp' + 'p' + 'p',
+    'ur_seq_prep_ln_fwd_f32': 'ppppfpliippp' + 'pp' + 'pi' + 'p',
+    'ur_seq_prep_ln_bwd_f32': 'pppplii' + 'ppp' + 'pppp' + 'p' + 'pi' + 'p',
     'ur_add_ln_fwd_f32': 'plplppflipl' + 'pp' + 'p' + 'p',
     'ur_add_ln_bwd_f32': 'plppp' + 'pl' + 'pl' + 'li' + 'pl' + 'ppp' + 'p' + 'p',
     'ur_gemm_f32': 'iilllplplplpipliip',
@@ -40,7 +40,9 @@ SIGNATURES = {
     'ur_count_positive_i32': 'plpp',
     'ur_loss_finish_f32': 'plpfppp',
     'ur_rowlist_link': 'ppillpppl' + 'p',
-    'ur_rowlist_apply_f32': 'pppi' + 'pppp' + 'l' + 'plpl' + 'l' + 'plpl' + 'i' + 'fffff' + 'ppp' + 'p' + 'ppi' + 'p',
+    'ur_rowlist_apply_f32': 'pppi' + 'pppp' + 'l' + 'plpl' + 'l' + 'plpl' + 'i' + 'fffff' + 'ppp' + 'p' + 'ppi' + 'pl' + 'p',
+    'ur_ipc_export': 'ppp',
+    'ur_ipc_open': 'plp',
     'ur_dense_opt_f32': 'ppppl' + 'i' + 'fffff' + 'ppp' + 'p',
     'ur_sqnorm_accum_f32': 'plpp',
     'ur_clip_coef_f32': 'pfpp',

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(256) seq_prep_ln_fwd_kernel(const float4* __re
                                                               float eps, const int32_t* __restrict__ seq, int64_t rows, int L, int d4,
                                                               float4* __restrict__ Y, float* __restrict__ mean_out,
                                                               float* __restrict__ rstd_out, const int32_t* __restrict__ tok_src,
-                                                              const int32_t* __restrict__ n_tok_dev) {
+                                                              const int32_t* __restrict__ n_tok_dev,
+                                                              const long long* __restrict__ shard_ptrs, int shard_world) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -74,12 +75,15 @@ __global__ void __launch_bounds__(256) seq_prep_ln_fwd_kernel(const float4* __re
         const int64_t src = tok_src ? (int64_t)__ldg(tok_src + r) : r;
         const int64_t id = __ldg(seq + src);
         const int l = (int)(src % L);
+        // row-sharded table: the row lives on rank id % W at local index id / W, read straight from the peer's HBM over NVLink
+        const float4* trow = shard_ptrs ? reinterpret_cast<const float4*>(shard_ptrs[id % shard_world]) + (id / shard_world) * d4
+                                        : table + id * d4;
         RowRegs<MAXV> x;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             int c = lane + 32 * i;
             if (c < d4) {
-                x.v[i] = ldg_stream(table + id * d4 + c);
+                x.v[i] = ldg_stream(trow + c);
                 if (pos) x.v[i] = f4_add(x.v[i], __ldg(pos + (int64_t)l * d4 + c));
             }
         }
@@ -162,7 +166,8 @@ __global__ void __launch_bounds__(256) seq_prep_ln_bwd_kernel(const float4* __re
                                                               const float* __restrict__ rstd_in, const float4* __restrict__ dY,
                                                               float4* __restrict__ dX, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ dpos,
-                                                              const int32_t* __restrict__ tok_inv) {
+                                                              const int32_t* __restrict__ tok_inv,
+                                                              const long long* __restrict__ shard_ptrs, int shard_world) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31;
     const int l = blockIdx.y;
@@ -177,12 +182,14 @@ __global__ void __launch_bounds__(256) seq_prep_ln_bwd_kernel(const float4* __re
         const int64_t t = tok_inv ? (int64_t)__ldg(tok_inv + r) : r;
         if (t < 0) continue;
         const int64_t id = __ldg(seq + r);
+        const float4* trow = shard_ptrs ? reinterpret_cast<const float4*>(shard_ptrs[id % shard_world]) + (id / shard_world) * d4
+                                        : table + id * d4;
         RowRegs<MAXV> x, dy, dx;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             int c = lane + 32 * i;
             if (c < d4) {
-                x.v[i] = ldg_stream(table + id * d4 + c);
+                x.v[i] = ldg_stream(trow + c);
                 if (pos) x.v[i] = f4_add(x.v[i], __ldg(pos + (int64_t)l * d4 + c));
                 dy.v[i] = dY[t * d4 + c];
             }
@@ -315,7 +322,8 @@ extern "C" {
 
 int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* gamma, const float* beta, float eps,
                            const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd,
-                           const int32_t* tok_src, const int32_t* n_tok_dev, void* stream) {
+                           const int32_t* tok_src, const int32_t* n_tok_dev, const void* shard_ptrs, int shard_world, void* stream) {
+    if (shard_ptrs && shard_world < 1) return UR_ERR_BAD_ARG;
     if (d <= 0 || (d & 3)) return UR_ERR_BAD_ARG;
     const int64_t rows = B * L;
     if (rows == 0) return UR_OK;
@@ -324,7 +332,7 @@ int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* ga
 #define CALL(MV)                                                                                                    \
     ur::seq_prep_ln_fwd_kernel<MV><<<ur::ln_grid(rows), 256, 0, st>>>(                                              \
         (const float4*)table, (const float4*)pos, (const float4*)gamma, (const float4*)beta, eps, item_seq, rows, L, d4, \
-        (float4*)Y, mean, rstd, tok_src, n_tok_dev);
+        (float4*)Y, mean, rstd, tok_src, n_tok_dev, (const long long*)shard_ptrs, shard_world);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();
@@ -332,7 +340,8 @@ int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* ga
 
 int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* gamma, const int32_t* item_seq, int64_t B, int L,
                            int d, const float* mean, const float* rstd, const float* dY, float* dX, float* dgamma, float* dbeta,
-                           float* dpos, const int32_t* tok_inv, void* stream) {
+                           float* dpos, const int32_t* tok_inv, const void* shard_ptrs, int shard_world, void* stream) {
+    if (shard_ptrs && shard_world < 1) return UR_ERR_BAD_ARG;
     if (d <= 0 || (d & 3)) return UR_ERR_BAD_ARG;
     if (B * L == 0) return UR_OK;
     const int d4 = d / 4;
@@ -344,7 +353,7 @@ int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* ga
 #define CALL(MV)                                                                                               \
     ur::seq_prep_ln_bwd_kernel<MV><<<grid, 256, d * sizeof(float), st>>>(                                      \
         (const float4*)table, (const float4*)pos, (const float4*)gamma, item_seq, B, L, d4, mean, rstd,        \
-        (const float4*)dY, (float4*)dX, dgamma, dbeta, dpos, tok_inv);
+        (const float4*)dY, (float4*)dX, dgamma, dbeta, dpos, tok_inv, (const long long*)shard_ptrs, shard_world);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();

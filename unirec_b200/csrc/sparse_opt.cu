@@ -18,6 +18,8 @@ struct RowSource {
     const float* coef;    // per-entry (coef_group == 1) or per-source-row coefficient, or null (= 1)
     int64_t src_group;    // entries per source row
     int64_t coef_group;   // entries per coefficient
+    const long long* part_ptrs;   // optional: source rows live in `part_rows`-row buffers on different GPUs (peer pointers, p2p.cu):
+    int64_t part_rows;            // source row q is row q % part_rows of buffer part_ptrs[q / part_rows]
 };
 
 __global__ void __launch_bounds__(256) rowlist_link_kernel(int32_t* __restrict__ head, const void* __restrict__ keys, int idx64,
@@ -116,7 +118,9 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
             const RowSource& s = first ? s0 : s1;
             const int64_t el = first ? e : e - n0;
             const float c = s.coef ? __ldg(s.coef + el / s.coef_group) : 1.f;
-            const float4* row = reinterpret_cast<const float4*>(s.src) + (el / s.src_group) * D4;
+            const int64_t q = el / s.src_group;
+            const float4* row = s.part_ptrs ? reinterpret_cast<const float4*>(s.part_ptrs[q / s.part_rows]) + (q % s.part_rows) * D4
+                                            : reinterpret_cast<const float4*>(s.src) + q * D4;
             const int32_t nx = __ldg(next + e);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) g[v] = f4_fma(c, __ldg(row + v * LPR + col), g[v]);
@@ -235,11 +239,14 @@ int ur_rowlist_apply_f32(float* table, float* mom, float* var, int d, int32_t* h
                          int64_t coef0_group, int64_t n0, const float* src1, int64_t src1_group, const float* coef1,
                          int64_t coef1_group, int mode, float lr, float beta1, float beta2, float eps, float weight_decay,
                          const int32_t* step_dev, const float* grad_scale_dev, const int32_t* skip_flag, float* sqnorm_out,
-                         const int32_t* u_begin_dev, const int32_t* u_end_dev, int small_ctas, void* stream) {
+                         const int32_t* u_begin_dev, const int32_t* u_end_dev, int small_ctas, const void* src1_part_ptrs,
+                         int64_t src1_part_rows, void* stream) {
+    if (src1_part_ptrs && src1_part_rows < 1) return UR_ERR_BAD_ARG;
     if (d <= 0 || (d & 3) || mode < 0 || mode > 3) return UR_ERR_BAD_ARG;
     if (max_uniq == 0) return UR_OK;
-    ur::RowSource s0{src0, coef0, src0_group > 0 ? src0_group : 1, coef0_group > 0 ? coef0_group : 1};
-    ur::RowSource s1{src1, coef1, src1_group > 0 ? src1_group : 1, coef1_group > 0 ? coef1_group : 1};
+    ur::RowSource s0{src0, coef0, src0_group > 0 ? src0_group : 1, coef0_group > 0 ? coef0_group : 1, nullptr, 1};
+    ur::RowSource s1{src1, coef1, src1_group > 0 ? src1_group : 1, coef1_group > 0 ? coef1_group : 1,
+                     (const long long*)src1_part_ptrs, src1_part_rows > 0 ? src1_part_rows : 1};
     ur::OptHyper h{lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale_dev, skip_flag};
     const int rpw = d >= 128 ? 1 : 128 / d;
     // small_ctas: 128-thread CTAs (6 K registers) that fit next to a resident persistent GEMM CTA when this launch runs on a

@@ -113,10 +113,13 @@ class RowGrad:
             self.n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
             self.n_hist = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def add(self, keys, src, src_group=1, coef=None, coef_group=1):
+    def add(self, keys, src, src_group=1, coef=None, coef_group=1, parts=None):
+        """parts = (int64 device tensor of peer pointers, rows per part): the source rows live in per-rank buffers (sharding.py)."""
         if len(self.specs) >= 2:
             raise RuntimeError('a table takes at most two gradient sources per step')
-        self.specs.append((keys, src, int(src_group), coef, int(coef_group)))
+        if parts is not None and not self.specs:
+            raise RuntimeError('a multi-part source must be the second gradient source of a table')
+        self.specs.append((keys, src, int(src_group), coef, int(coef_group), parts))
 
     def n_entries(self):
         return sum(k.numel() for k, *_ in self.specs)
@@ -134,12 +137,14 @@ class RowGrad:
         self.linked = True
 
     def sources(self):
-        return [(src, sg, coef, cg, keys.numel()) for keys, src, sg, coef, cg in self.specs]
+        return [(src, sg, coef, cg, keys.numel(), parts) for keys, src, sg, coef, cg, parts in self.specs]
 
     def to_dense(self):
         """Exact-dense mode: materialise the [V,d] gradient the reference's autograd would produce."""
         g = torch.zeros_like(self.param.data)
-        for keys, src, sg, coef, cg in self.specs:
+        for keys, src, sg, coef, cg, parts in self.specs:
+            if parts is not None:
+                raise RuntimeError('dense table gradients are not available with peer-memory gradient sources')
             ops.scatter_add_rows(g, keys, src, sg, coef, cg, pad_id=self.pad_id)
         return g
 
@@ -233,7 +238,7 @@ class SASRecTower:
         x = ws.get('x0', (T, d))
         self.mean0, self.rstd0 = ws.get('mean0', (T,)), ws.get('rstd0', (T,))
         ops.seq_prep_ln_fwd(table, pos, fp.p('LayerNorm.weight'), fp.p('LayerNorm.bias'), self.eps, index, x,
-                            self.mean0, self.rstd0, tok_src=pk['tok_src'], n_tok=pk['n'])
+                            self.mean0, self.rstd0, tok_src=pk['tok_src'], n_tok=pk['n'], shards=eng.seq_shards)
         self.saved = []
         self.item_seq, self.pk = item_seq, pk
         user = ws.get('user_emb', (B, d))
@@ -330,7 +335,8 @@ class SASRecTower:
         drows = ws.get('drows', (T, d))
         ops.seq_prep_ln_bwd(table, pos, fp.p('LayerNorm.weight'), index, self.mean0, self.rstd0, dx, drows,
                             fp.g('LayerNorm.weight'), fp.g('LayerNorm.bias'),
-                            fp.g('position_embedding.weight') if self.causal else None, tok_inv=pk['tok_inv'])
+                            fp.g('position_embedding.weight') if self.causal else None, tok_inv=pk['tok_inv'],
+                            shards=eng.seq_shards)
         eng.add_seq_rowgrad(item_seq, drows)
 
     def _layer_bwd_full(self, i, st, dx, item_seq, pk):
@@ -525,6 +531,7 @@ class Engine:
         self.nan_flag = None
         self.last = None
         # stream-level overlap of the table update with the encoder backward (set up by the Trainer, see _early_link)
+        self.seq_shards = None            # (peer pointers, W) when the history table is row-sharded and read over NVLink (sharding.py)
         self.overlap_hook = None          # FusedOptimizer (provides early_apply) or None
         self.overlap_mode = 1             # 1: link the row lists on a side stream during the forward pass;
                                           # 2: also update the target-only rows on the side stream during the backward pass

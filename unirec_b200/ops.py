@@ -106,20 +106,41 @@ def _i32(t):
     return _ptr(t, torch.int32) if t is not None else None
 
 
-def seq_prep_ln_fwd(table, pos, gamma, beta, eps, item_seq, Y, mean, rstd, tok_src=None, n_tok=None):
+def seq_prep_ln_fwd(table, pos, gamma, beta, eps, item_seq, Y, mean, rstd, tok_src=None, n_tok=None, shards=None):
+    """shards = (int64 device tensor of W peer pointers, W): `item_seq` holds global ids of a row-sharded table."""
     B, L = item_seq.shape
     _call('ur_seq_prep_ln_fwd_f32', _f32(table), _f32(pos), _f32(gamma), _f32(beta), float(eps),
           _ptr(item_seq, torch.int32), B, L, table.shape[1], _f32(Y), _f32(mean), _f32(rstd), _i32(tok_src), _i32(n_tok),
-          _stream())
+          _ptr(shards[0], torch.int64) if shards else None, int(shards[1]) if shards else 0, _stream())
     return Y
 
 
-def seq_prep_ln_bwd(table, pos, gamma, item_seq, mean, rstd, dY, dX, dgamma, dbeta, dpos, tok_inv=None):
+def seq_prep_ln_bwd(table, pos, gamma, item_seq, mean, rstd, dY, dX, dgamma, dbeta, dpos, tok_inv=None, shards=None):
     B, L = item_seq.shape
     _call('ur_seq_prep_ln_bwd_f32', _f32(table), _f32(pos), _f32(gamma), _ptr(item_seq, torch.int32), B, L,
           table.shape[1], _f32(mean), _f32(rstd), _f32(dY), _f32(dX), _f32(dgamma), _f32(dbeta), _f32(dpos), _i32(tok_inv),
-          _stream())
+          _ptr(shards[0], torch.int64) if shards else None, int(shards[1]) if shards else 0, _stream())
     return dX
+
+
+def ipc_export(t):
+    """(64-byte CUDA IPC handle, byte offset) of a device tensor, for mapping it into the peer processes (csrc/p2p.cu)."""
+    import ctypes
+    h = ctypes.create_string_buffer(64)
+    off = ctypes.c_int64(0)
+    _cabi.check(_cabi.lib().ur_ipc_export(_ptr(t), ctypes.cast(h, ctypes.c_void_p), ctypes.cast(ctypes.byref(off), ctypes.c_void_p)),
+                'ur_ipc_export')
+    return bytes(h.raw), int(off.value)
+
+
+def ipc_open(handle, offset):
+    """Device pointer (int) of a peer's exported buffer."""
+    import ctypes
+    h = ctypes.create_string_buffer(handle, 64)
+    out = ctypes.c_int64(0)
+    _cabi.check(_cabi.lib().ur_ipc_open(ctypes.cast(h, ctypes.c_void_p), int(offset), ctypes.cast(ctypes.byref(out), ctypes.c_void_p)),
+                'ur_ipc_open')
+    return int(out.value)
 
 
 def pack_tokens(item_seq, offs, tok_src, tok_inv, last_tok, n_tok, keep_all=False):
@@ -258,9 +279,10 @@ def rowlist_link(head, keys, entry_offset, nxt, uniq, n_uniq, pad_id=0):
 def rowlist_apply(table, mom, var, head, nxt, uniq, n_uniq, max_uniq, sources, mode, lr=0.0, beta1=0.9, beta2=0.999,
                   eps=1e-8, weight_decay=0.0, step_dev=None, grad_scale_dev=None, skip_flag=None, sqnorm_out=None,
                   u_begin=None, u_end=None, small_ctas=False):
-    """sources: list of 1 or 2 tuples (src, src_group, coef_or_None, coef_group, n_entries)."""
+    """sources: list of 1 or 2 tuples (src, src_group, coef_or_None, coef_group, n_entries[, (peer_ptrs int64 [W], rows_per_part)])."""
     s0 = sources[0]
     s1 = sources[1] if len(sources) > 1 else (None, 1, None, 1, 0)
+    parts = s1[5] if len(s1) > 5 else None
     _call('ur_rowlist_apply_f32', _f32(table), _f32(mom), _f32(var), table.shape[1], _ptr(head, torch.int32),
           _ptr(nxt, torch.int32), _ptr(uniq, torch.int32), _ptr(n_uniq, torch.int32), max_uniq,
           _f32(s0[0]), s0[1], _f32(s0[2]), s0[3], s0[4], _f32(s1[0]), s1[1], _f32(s1[2]), s1[3],
@@ -268,7 +290,8 @@ def rowlist_apply(table, mom, var, head, nxt, uniq, n_uniq, max_uniq, sources, m
           _ptr(step_dev, torch.int32) if step_dev is not None else None, _f32(grad_scale_dev),
           _ptr(skip_flag, torch.int32) if skip_flag is not None else None, _f32(sqnorm_out),
           _ptr(u_begin, torch.int32) if u_begin is not None else None,
-          _ptr(u_end, torch.int32) if u_end is not None else None, int(small_ctas), _stream())
+          _ptr(u_end, torch.int32) if u_end is not None else None, int(small_ctas),
+          _ptr(parts[0], torch.int64) if parts else None, int(parts[1]) if parts else 0, _stream())
 
 
 def dense_opt(param, grad, mom, var, mode, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step_dev=None,

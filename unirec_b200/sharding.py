@@ -119,6 +119,10 @@ class ShardedEngine(Engine):
             raise ValueError('row-sharded tables are implemented for the SASRec and GRU towers')
         if model.loss_type != 'softmax':
             raise ValueError('row-sharded tables are implemented for loss_type=softmax')
+        # peer-memory mode (SASRec tower): history rows and their gradients are read straight from the owner / requester GPU over
+        # NVLink (CUDA IPC mappings, csrc/p2p.cu) instead of a zero-filled [W, B*L, d] reduce-scatter and a [W, B*L, d] all-gather
+        self.p2p = bool(int(model.config.get('shard_p2p', 1))) and tower_kind == 'sasrec' and self.world > 1
+        self._peer_cache = {}
 
     def rowgrad(self, param):
         rg = super().rowgrad(param)
@@ -137,12 +141,33 @@ class ShardedEngine(Engine):
         dist.reduce_scatter_tensor(out, t, op=dist.ReduceOp.SUM, group=self.group)
         return out
 
+    # ---- peer memory ------------------------------------------------------------------------------
+    def _peer_ptrs(self, name, t):
+        """int64 device tensor [W]: pointers to every rank's buffer `name` (same shape everywhere), mapped through CUDA IPC.
+        Collective on first use per buffer; the mappings live as long as the process."""
+        key = (name, t.data_ptr(), tuple(t.shape))
+        ptrs = self._peer_cache.get(key)
+        if ptrs is None:
+            handle, off = ops.ipc_export(t)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (handle, off), group=self.group)
+            vals = [t.data_ptr() if w == self.rank else ops.ipc_open(h, o) for w, (h, o) in enumerate(gathered)]
+            ptrs = torch.tensor(vals, dtype=torch.int64, device=self.device)
+            self._peer_cache[key] = ptrs
+        return ptrs
+
     # ---- sequence rows ----------------------------------------------------------------------------
     def seq_rows_source(self, item_seq):
         B, L = item_seq.shape
         d = self.table_for_seq().shape[1]
         seq_all = self._all_gather('seq', item_seq)                       # [W, B, L]
         self.seq_all = seq_all
+        if self.p2p:
+            # The all-gather above doubles as the step barrier: it completes only after every rank has enqueued it, i.e. after
+            # every rank's previous table update -- the peers' shards are stable until their next optimizer step, which comes
+            # after the all-reduce of the encoder gradients (= after every rank's backward pass has read them again).
+            self.seq_shards = (self._peer_ptrs('table', self.table_for_seq().data), self.world)
+            return self.table_for_seq().data, item_seq
         rows = self.ws.get('seq_rows_all', (self.world, B * L, d))
         ops.shard_gather_rows(self.table_for_seq().data, seq_all, self.world, self.rank, rows)
         mine = self._reduce_scatter('seq_rows', rows)                     # [B*L, d] rows of the local batch
@@ -153,9 +178,17 @@ class ShardedEngine(Engine):
         return mine, index
 
     def add_seq_rowgrad(self, item_seq, drows):
-        d_all = self._all_gather('drows', drows)                           # [W, B*L, d]
         keys = self.ws.get('seq_keys_local', (self.seq_all.numel(),), dtype=torch.int32)
         ops.shard_localize(self.seq_all, self.world, self.rank, keys, pad_id=0)
+        if self.p2p:
+            # owners pull the gradient rows of their history entries from the requesters' `drows` buffers inside the optimizer
+            # kernel (entry e of rank w's batch = row e of w's buffer).  Ordering: the optimizer runs after the all-reduce of the
+            # encoder gradients (every rank has finished writing drows); a rank overwrites drows only after the next step's
+            # first all-gather (every rank has finished reading it).
+            parts = (self._peer_ptrs('drows', drows), drows.shape[0])
+            self.rowgrad(self.table_for_seq()).add(keys, drows, 1, None, 1, parts=parts)
+            return
+        d_all = self._all_gather('drows', drows)                           # [W, B*L, d]
         self.rowgrad(self.table_for_seq()).add(keys, d_all.view(-1, d_all.shape[-1]), 1, None, 1)
 
     # ---- forward / backward ---------------------------------------------------------------------
