@@ -123,6 +123,8 @@ class ShardedEngine(Engine):
         # NVLink (CUDA IPC mappings, csrc/p2p.cu) instead of a zero-filled [W, B*L, d] reduce-scatter and a [W, B*L, d] all-gather
         self.p2p = bool(int(model.config.get('shard_p2p', 1))) and tower_kind == 'sasrec' and self.world > 1
         self._peer_cache = {}
+        self._prefetch = None           # (item_id, label, user_id) whose all-gathers are issued asynchronously under the tower
+        self._pending = None
 
     def rowgrad(self, param):
         rg = super().rowgrad(param)
@@ -134,6 +136,25 @@ class ShardedEngine(Engine):
         out = self.ws.get('ag_' + name, (self.world,) + tuple(t.shape), dtype=t.dtype)
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
+
+    def _all_gather_async(self, name, t):
+        """all-gather on NCCL's stream, not waited for: (output, work, input kept alive)."""
+        out = self.ws.get('ag_' + name, (self.world,) + tuple(t.shape), dtype=t.dtype)
+        t = t.contiguous()
+        work = dist.all_gather_into_tensor(out, t, group=self.group, async_op=True)
+        return out, work, t
+
+    def _launch_prefetch(self):
+        """The target / label id matrices (the bulk of the bytes all-gathered per step) do not depend on the encoder: their
+        all-gathers start right after the small history-id gather and run on NCCL's stream while the tower computes."""
+        if self._prefetch is None:
+            return
+        item_id, label, user_id = self._prefetch
+        self._prefetch = None
+        pend = {'ids': self._all_gather_async('ids', item_id), 'label': self._all_gather_async('label', label)}
+        if user_id is not None:
+            pend['uid'] = self._all_gather_async('uid', user_id)
+        self._pending = pend
 
     def _reduce_scatter(self, name, t):
         """t: [W, ...] -> sum over ranks of slice [rank]."""
@@ -162,6 +183,7 @@ class ShardedEngine(Engine):
         d = self.table_for_seq().shape[1]
         seq_all = self._all_gather('seq', item_seq)                       # [W, B, L]
         self.seq_all = seq_all
+        self._launch_prefetch()
         if self.p2p:
             # The all-gather above doubles as the step barrier: it completes only after every rank has enqueued it, i.e. after
             # every rank's previous table update -- the peers' shards are stable until their next optimizer step, which comes
@@ -203,15 +225,21 @@ class ShardedEngine(Engine):
         B, N = item_id.shape
         for rg in self._rowgrads.values():
             rg.reset()
-        user = self.tower.forward(item_seq=item_seq, item_seq_len=item_seq_len, user_id=user_id, save=True)
-        d = user.shape[1]
-        S = W * B
-        ids_all = self._all_gather('ids', item_id).view(S, N)
         if label is None:
             label = ws.get('default_label', (B, N), dtype=torch.int32, zero=True)
             label[:, 0] = 1
-        lab_all = self._all_gather('label', label.contiguous()).view(S, N)
-        uid_all = self._all_gather('uid', user_id).view(S) if (m.has_user_bias and user_id is not None) else None
+        need_uid = m.has_user_bias and user_id is not None
+        self._prefetch, self._pending = (item_id, label.contiguous(), user_id if need_uid else None), None
+        user = self.tower.forward(item_seq=item_seq, item_seq_len=item_seq_len, user_id=user_id, save=True)
+        d = user.shape[1]
+        S = W * B
+        self._launch_prefetch()                      # (towers that did not go through seq_rows_source)
+        pend, self._pending = self._pending, None
+        for out, work, _keep in pend.values():
+            work.wait()                              # the compute stream waits for NCCL's stream here
+        ids_all = pend['ids'][0].view(S, N)
+        lab_all = pend['label'][0].view(S, N)
+        uid_all = pend['uid'][0].view(S) if need_uid else None
         u_all = self._all_gather('user', user).view(S, d)
         n_pos = ws.get('n_pos', (1,))
         ops.count_positive(lab_all, n_pos)                                  # global positives: same value on every rank
