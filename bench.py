@@ -254,8 +254,8 @@ def main():
     value = samples / (ms_total / 1e3)
     algo_bytes = B * (1 + K) * d * 4                     # target/negative rows read once by the fused score kernel
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed `ncu --set full` capture
-    # (profiles/r01c_full_captures.csv: 542.5 MB + 9.8 MB); only known for the default workload on one GPU
-    traffic = 552.3e6 if (args.workload == DEFAULT_WORKLOAD and world == 1) else None
+    # (profiles/r01d_full_captures.csv: 542.5 MB + 10.7 MB); only known for the default workload on one GPU
+    traffic = 553.2e6 if (args.workload == DEFAULT_WORKLOAD and world == 1) else None
     k_ms = statistics.mean(kernel_ms) if kernel_ms else float('nan')
     achieved = algo_bytes / (k_ms / 1e3) / 1e9
     line = {
