@@ -279,7 +279,7 @@ def main():
                      'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': k_ms},
         'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N=1 only
         from oracle import cpu_baseline
         cfgo = dict(COMMON)
         cfgo.update({k: v for k, v in w.items() if k not in ('K', 'B')})
