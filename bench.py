@@ -17,7 +17,6 @@ import statistics
 import subprocess
 import sys
 import threading
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -205,16 +204,18 @@ def main():
     final_loss = float(loss)
 
     # ---- same device-resident steps through the captured CUDA graph (Trainer.train_step's steady state) ----
-    for i in range(3):
-        trainer.train_step(resident[i % n_pool])
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for i in range(args.steps):
-        trainer.train_step(resident[(args.warmup + i) % n_pool])
-    g1.record()
-    barrier()
-    ms_graph = g0.elapsed_time(g1)
+    ms_graph = float('nan')
+    if world == 1 and not args.no_graph:          # the row-sharded step (N > 1) is not graph-captured yet
+        for i in range(3):
+            trainer.train_step(resident[i % n_pool])
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            trainer.train_step(resident[(args.warmup + i) % n_pool])
+        g1.record()
+        barrier()
+        ms_graph = g0.elapsed_time(g1)
 
     # ---- end-to-end arm: pinned host inputs in, loss out, every step, through the public Trainer API ----
     # Trainer.device_batches is the loader-side API of the trainer: it copies batch i+1 host->device on a copy stream while
@@ -270,7 +271,7 @@ def main():
         'e2e': {'value': samples / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'value_cuda_graph': {'value': samples / (ms_graph / 1e3), 'unit': 'samples/s', 'ms_per_step': ms_graph / args.steps,
+        'value_cuda_graph': None if ms_graph != ms_graph else {'value': samples / (ms_graph / 1e3), 'unit': 'samples/s', 'ms_per_step': ms_graph / args.steps,
                              'note': 'device-resident inputs, whole step replayed as one CUDA graph (the timed `value` region runs '
                                      'eagerly so that the roofline kernel can be bracketed by CUDA events)'},
         'roofline': {'kernel': 'score_loss_kernel (fused gather+dot+softmax+grad)' if world == 1 else

@@ -10,7 +10,6 @@ One engine per model instance.  It owns
 Reference call stack being replaced: BaseRecommender.forward -> forward_item_emb / forward_user_emb / _predict_layer /
 _cal_loss (unirec/model/base/recommender.py:46-96, reco_abc.py:220-272) and its autograd.
 """
-import math
 from typing import Dict, List, Optional
 
 import torch
