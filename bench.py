@@ -265,7 +265,10 @@ def main():
         'vs_baseline': None, 'dtype': 'tf32' if args.gemm_precision == 'tf32' else 'f32', 'data': 'synthetic',
         'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'seq_len': L, 'n_items': w['n_items'],
                    'n_neg': K, 'optimizer': 'adam: row-sparse (lazy) on tables, flat dense on encoder', 'dropout': 0.0,
-                   'gemm_precision': args.gemm_precision, 'l2': 'inputs larger than L2: %.1f GB table, random rows, %d rotating batches'
+                   'gemm_precision': args.gemm_precision,
+                   'encoder': 'live positions only (pack_sequences=1) and last layer on B rows (trim_last_layer=1): dead rows of the '
+                              'reference computation are not computed, outputs and gradients identical (tests)',
+                   'l2': 'inputs larger than L2: %.1f GB table, random rows, %d rotating batches'
                    % (w['n_items'] * d * 4 / 1e9, n_pool), 'parallelism': 'dp%d' % world, 'final_loss': final_loss},
         'clocks': clk,
         'e2e': {'value': samples / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
