@@ -92,3 +92,22 @@ def test_rank_metrics():
     assert res['ndcg@3'] == pytest.approx((1.0 + 0.5) / 3)
     assert res['mrr'] == pytest.approx((1 + 1 / 3 + 1 / 6) / 3)
     assert res['group_auc'] == pytest.approx((1.0 + 0.8 + 0.5) / 3)
+
+
+def test_rank_metrics_match_reference_evaluator_golden():
+    """§8 f3: hit / ndcg / mrr / group_auc from ranks equal the reference's OnePositiveEvaluator on the same score matrices
+    (fixture written by oracle/make_eval_golden.py from unirec/facility/evaluation/onepos.py:104-175)."""
+    import os
+    import numpy as np
+    from unirec_b200.facility.evaluation import RankEvaluator
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden_eval', 'onepos_metrics.npz'))
+    metrics_str = bytes(z['metrics_str']).decode()
+    ev = RankEvaluator(metrics_str)
+    for tag in ('a', 'b'):
+        scores = torch.from_numpy(z['scores_' + tag])
+        rank = (scores[:, 1:] > scores[:, :1]).sum(1).double()          # one_vs_k rank, as RankEvaluator._ranks computes it
+        res = ev.metrics_from_ranks(rank, scores.shape[1])
+        ref = {k.split('/', 1)[1]: float(z[k]) for k in z.files if k.startswith('metric_%s/' % tag)}
+        assert set(ref) == set(res), (sorted(ref), sorted(res))
+        for k, v in ref.items():
+            assert res[k] == pytest.approx(v, rel=1e-6, abs=1e-9), (tag, k, res[k], v)
