@@ -170,3 +170,27 @@ def test_main_run_end_to_end(tmp_path):
                          metrics="['hit@5', 'ndcg@5', 'group_auc']", key_metric='group_auc', gpu_id=-1))
     assert res['group_auc'] > 0.75, res            # the planted (user mod 7 == item mod 7) pattern is learnable
     assert os.path.exists(str(tmp_path / 'out' / 'result_e2e.tsv'))
+
+
+@pytest.mark.parametrize('tag,kw', [('unorder', dict(mask_mode='unorder')), ('auto_last', dict(mask_mode='autoregressive', seq_last=1)),
+                                    ('maxlen', dict(mask_mode='autoregressive', data_format='user-item-max_len'))])
+def test_history_transform_matches_reference_golden(tag, kw):
+    """a15: AddUserHistory + the dataset's left-padding reproduce the reference transform (fixture written by
+    oracle/make_data_golden.py from unirec/data/transform/adduserhistory.py:32-73) on 200 samples, including users without history,
+    user ids beyond the table, duplicated history items and targets that occur several times in the history."""
+    from unirec_b200.data.dataset.seqrecdataset import SeqRecDataset
+    from unirec_b200.data.transform.adduserhistory import AddUserHistory
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden_eval', 'history_transform.npz'))
+    n_users, L = int(z['n_users']), int(z['L'])
+    hist = np.empty(n_users, dtype=object)
+    for u in range(n_users):
+        h = z['hist/%d' % u]
+        hist[u] = h if len(h) else None
+    tr = AddUserHistory(hist, **kw)
+    ds = SeqRecDataset.__new__(SeqRecDataset)
+    ds.config = {'max_seq_len': L}
+    for i, u in enumerate(z['users']):
+        sample = (int(u), int(z['targets'][i]), int(z['maxlens'][i])) if tag == 'maxlen' else (int(u), int(z['targets'][i]))
+        h, n, _ = tr(sample)
+        assert np.array_equal(ds._padding(np.asarray(h)), z['seq/' + tag][i]), (tag, i, h, z['seq/' + tag][i])
+        assert min(int(n), L) == int(z['len/' + tag][i]), (tag, i)
