@@ -111,3 +111,14 @@ def test_rank_metrics_match_reference_evaluator_golden():
         assert set(ref) == set(res), (sorted(ref), sorted(res))
         for k, v in ref.items():
             assert res[k] == pytest.approx(v, rel=1e-6, abs=1e-9), (tag, k, res[k], v)
+
+
+def test_hot_path_switches_have_documented_defaults():
+    """The B200-specific config keys (DESIGN.md sections 4-5) parse from base.yaml with the defaults the bench runs with, and
+    command-line / dict overrides reach the config like any reference key."""
+    cfg = argument_parser.parse_arguments({'model': 'SASRec', 'dataset': 'example'}, argv=[])
+    assert cfg['gemm_precision'] == 'tf32x3' and int(cfg['pack_sequences']) == 1 and int(cfg['trim_last_layer']) == 1
+    assert cfg.get('table_update', 'sparse') == 'sparse'
+    cfg = argument_parser.parse_arguments({'model': 'SASRec', 'dataset': 'example', 'pack_sequences': 0},
+                                          argv=['--gemm_precision=fp32', '--trim_last_layer=0'])
+    assert cfg['gemm_precision'] == 'fp32' and int(cfg['pack_sequences']) == 0 and int(cfg['trim_last_layer']) == 0

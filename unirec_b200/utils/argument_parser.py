@@ -31,7 +31,10 @@ _FLAGS = {
           'use_pre_item_emb', 'use_position_emb', 'max_seq_len', 'has_user_bias', 'has_item_bias', 'hidden_size', 'inner_size',
           'n_layers', 'asymmetric', 'conv_size', 'seq_merge', 'encoder_dims', 'decoder_dims', 'total_anneal_steps',
           'eval_reparameter_sampling_times', 'freeze', 'enable_morec', 'morec_ngroup',
-          'n_heads', 'n_users', 'n_items', 'has_user_emb'],
+          'n_heads', 'n_users', 'n_items', 'has_user_emb',
+          # unirec_b200 additions
+          'pack_sequences', 'trim_last_layer', 'cuda_graph', 'overlap_table_update', 'shard_p2p', 'table_shard_world',
+          'table_shard_rank'],
     float: ['grad_clip_value', 'score_clip_value', 'init_std', 'init_mean', 'scheduler_factor', 'learning_rate',
             'neg_by_pop_alpha', 'dropout_prob', 'hidden_dropout_prob', 'attn_dropout_prob', 'ccl_w', 'ccl_m', 'weight_decay',
             'layer_norm_eps', 'tau', 'user_sequence_alpha', 'seq_decay', 'init_ratio', 'anneal_cap', 'l1_coef', 'l2_coef',
