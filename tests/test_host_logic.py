@@ -1,5 +1,6 @@
 """CPU: host-side logic of the drop-in boundary -- config precedence, registry, seed-exact initialisation and
 state_dict names (vs the reference goldens), trainer control helpers, loud failure without CUDA."""
+import os
 import sys
 
 import pytest
@@ -122,3 +123,21 @@ def test_hot_path_switches_have_documented_defaults():
     cfg = argument_parser.parse_arguments({'model': 'SASRec', 'dataset': 'example', 'pack_sequences': 0},
                                           argv=['--gemm_precision=fp32', '--trim_last_layer=0'])
     assert cfg['gemm_precision'] == 'fp32' and int(cfg['pack_sequences']) == 0 and int(cfg['trim_last_layer']) == 0
+
+
+def test_install_as_unirec_alias_resolves_reference_imports():
+    """code written against the reference package (`from unirec.main import main`,
+    `get_class_instance(name, 'unirec/model')`) resolves to this package after `install_as_unirec()`.  Runs in a subprocess so the
+    alias does not leak into the other tests."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); import unirec_b200; unirec_b200.install_as_unirec();"
+            "from unirec.utils import general, argument_parser; from unirec.main import main;"
+            "import unirec.data.dataset, unirec.facility.trainer;"
+            "names = ['SASRec', 'GRU', 'AvgHist', 'SVDPlusPlus', 'MF'];"
+            "mods = [general.get_class_instance(n, 'unirec/model').__module__ for n in names];"
+            "assert all(m.startswith('unirec_b200.model.') for m in mods), mods;"
+            "assert callable(main.run); print('ALIAS_OK')" % root)
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120, cwd='/tmp')
+    assert res.returncode == 0 and 'ALIAS_OK' in res.stdout, res.stdout + res.stderr
