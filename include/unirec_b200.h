@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UR_ABI_VERSION 1
+#define UR_ABI_VERSION 2
 
 enum { UR_LOSS_SOFTMAX = 0, UR_LOSS_BPR = 1 };
 enum { UR_ACT_NONE = 0, UR_ACT_SWISH = 1, UR_ACT_GELU = 2, UR_ACT_RELU = 3, UR_ACT_TANH = 4, UR_ACT_SIGMOID = 5 };
@@ -51,23 +51,32 @@ int ur_pool_sum_fwd_f32(const float* table, int d, const int32_t* item_seq, int6
 int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos /*nullable*/, const float* gamma, const float* beta, float eps,
                            const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd,
                            const int32_t* tok_src /*nullable*/, const int32_t* n_tok_dev /*nullable*/,
-                           const void* shard_ptrs /*nullable: W peer pointers (int64) to the row shards*/, int shard_world, void* stream);
+                           const void* shard_ptrs /*nullable: W peer pointers (int64) to the row shards*/, int shard_world,
+                           const int64_t* rng /*nullable*/, float drop_p, int drop_site, void* stream);
 /* dX[B*L,d] = gradient wrt the gathered rows (feeds the row-sparse table update); dgamma/dbeta/dpos are ACCUMULATED */
 int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* gamma, const int32_t* item_seq, int64_t B, int L,
                            int d, const float* mean, const float* rstd, const float* dY, float* dX, float* dgamma, float* dbeta,
                            float* dpos /*nullable*/, const int32_t* tok_inv /*nullable*/, const void* shard_ptrs /*nullable*/,
-                           int shard_world, void* stream);
+                           int shard_world, const int64_t* rng /*nullable*/, float drop_p, int drop_site, void* stream);
 
-/* ---- K6: post-LN residual.  X <- X + R (kept for backward), Y = LayerNorm(X).
- * replaces: LayerNorm(hidden + input) unirec/model/modules.py:314, :353 */
+/* ---- K6: post-LN residual.  X <- dropout(X) + R (kept for backward), Y = LayerNorm(X).
+ * replaces: LayerNorm(dropout(hidden) + input) unirec/model/modules.py:313-314, :352-353
+ * Dropout (all ops below): rng = device int64[2] (seed, training step), drop_p in [0,1), drop_site = id of the nn.Dropout
+ * instance; rng == NULL or drop_p == 0 -> identity.  The mask of an element depends only on (seed, step, site, ORIGINAL token
+ * position, column) -- csrc/dropout.cuh -- so backward kernels regenerate it; the original position of row r is row_pos[r]
+ * (packed token map) or r * pos_mul + pos_add. */
 int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R /*nullable*/, int64_t ldr, const float* gamma, const float* beta,
                       float eps, int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd,
-                      const int32_t* rows_dev /*nullable*/, void* stream);
-/* dZ = LN'(Z) (dY + dExtra); dgamma/dbeta ACCUMULATED; dZ may alias dY; dzsum (nullable) += column sums of dZ, i.e. the
- * bias gradient of the linear layer whose output (plus residual) is Z */
+                      const int32_t* rows_dev /*nullable*/, const int64_t* rng /*nullable*/, float drop_p, int drop_site,
+                      const int32_t* row_pos /*nullable*/, int64_t pos_mul, int64_t pos_add, void* stream);
+/* dZ = LN'(Z) (dY + dExtra); dgamma/dbeta ACCUMULATED; dZ may alias dY; dzsum (nullable) += column sums of the gradient of the
+ * linear layer's output, i.e. its bias gradient.  With dropout, dZdrop = dZ * mask is that gradient (dZ keeps flowing down the
+ * residual branch); without, dZdrop is NULL and dZ serves both. */
 int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const float* mean, const float* rstd, const float* dY,
                       int64_t lddy, const float* dExtra /*nullable*/, int64_t ldde, int64_t rows, int d, float* dZ, int64_t lddz,
-                      float* dgamma, float* dbeta, float* dzsum /*nullable*/, const int32_t* rows_dev /*nullable*/, void* stream);
+                      float* dgamma, float* dbeta, float* dzsum /*nullable*/, const int32_t* rows_dev /*nullable*/,
+                      float* dZdrop /*nullable*/, int64_t lddzd, const int64_t* rng /*nullable*/, float drop_p, int drop_site,
+                      const int32_t* row_pos /*nullable*/, int64_t pos_mul, int64_t pos_add, void* stream);
 
 /* ---- K4/K7: C (+)= act(op(A) op(B) + bias); preact (nullable) receives the pre-activation for backward.
  * replaces: nn.Linear calls unirec/model/modules.py:285-287,312,348-351; gru.py:30-31
@@ -107,16 +116,18 @@ int ur_act_bwd_f32(float* dY, const float* preact, int64_t n, int act, void* str
 /* out[n] += sum_m X[m,n] (bias gradients) */
 int ur_colsum_accum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, const int32_t* rows_dev /*nullable*/, void* stream);
 
-/* ---- K5: fused attention on packed QKV [B*L, 3d] with the SASRec additive mask (-10000), L <= 256.
+/* ---- K5: fused attention on packed QKV [B*L, 3d] with the SASRec additive mask (-10000), L <= 256, head dim in
+ * {2,4,8,16,32,64,128} (stock SASRec.yaml: n_heads 16), attention-probability dropout (modules.py:307) by counter.
  * replaces: MultiHeadAttention.forward unirec/model/modules.py:289-311 and SASRec._get_attention_mask sasrec.py:40-57 */
 /* offs / tok_src (nullable, both or none): packed token layout of ur_pack_tokens (sample b owns rows [offs[b], offs[b+1]) of qkv / ctx).
  * q_last (nullable, with q_only_last): the single query per sample comes from a compact [B, d] buffer, ctx / dctx are compact
  * [B, d] too and dQ goes to dq_last [B, d]. */
 int ur_attn_fwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
-                    float* ctx, float* lse /*[B,H,L]*/, const int32_t* offs, const int32_t* tok_src, const float* q_last, void* stream);
+                    float* ctx, float* lse /*[B,H,L]*/, const int32_t* offs, const int32_t* tok_src, const float* q_last,
+                    const int64_t* rng /*nullable*/, float drop_p, int drop_site, void* stream);
 int ur_attn_bwd_f32(const float* qkv, const int32_t* item_seq, int64_t B, int L, int H, int dh, int causal, int q_only_last,
                     const float* ctx, const float* lse, const float* dctx, float* dqkv, const int32_t* offs, const int32_t* tok_src,
-                    const float* q_last, float* dq_last, void* stream);
+                    const float* q_last, float* dq_last, const int64_t* rng /*nullable*/, float drop_p, int drop_site, void* stream);
 
 /* ---- token packing for the sequence towers (csrc/pack.cu): live positions = real items + position L-1 (+ every position of a
  * sequence without real items).  replaces: nothing in the reference -- it computes all B*L positions (sasrec.py:59-76); the dead ones
@@ -125,6 +136,17 @@ int ur_pack_tokens(const int32_t* item_seq, int64_t B, int L, int keep_all, int3
                    int32_t* tok_inv /*[B*L]*/, int32_t* last_tok /*[B]*/, int32_t* n_tok /*[1]*/, void* stream);
 /* zero rows [*n_dev, roundup32(*n_dev)) of X[rows_cap, width] */
 int ur_zero_tail_rows_f32(float* X, int64_t ld, int width, const int32_t* n_dev, int64_t rows_cap, void* stream);
+
+/* ---- dropout outside the fused LN / attention kernels (csrc/dropout.cu).
+ * replaces: nn.Dropout on the gathered item embeddings, unirec/model/sequential/gru.py:29 (forward on the rows, backward on their
+ * gradient: the same call).  ur_dropout_mask_f32 writes the multipliers (0 or 1/(1-p)) of a site: flat = 0 -> [rows, d] by row
+ * position; flat = 1 -> rows*d consecutive elements (attention site: ((b*H+h)*L + i)*L + j).  Test hook: the CPU oracle takes them
+ * as explicit factors.  ur_rng_advance: rng[1] += 1 (one mask set per training step). */
+int ur_dropout_rows_f32(float* X, int64_t ld, int64_t rows, int d, const int32_t* row_pos /*nullable*/, int64_t pos_mul,
+                        int64_t pos_add, const int32_t* rows_dev /*nullable*/, const int64_t* rng, float p, int site, void* stream);
+int ur_dropout_mask_f32(float* out, int64_t rows, int d, const int32_t* row_pos /*nullable*/, int64_t pos_mul, int64_t pos_add,
+                        const int64_t* rng, float p, int site, int flat, void* stream);
+int ur_rng_advance(int64_t* rng, void* stream);
 
 /* ---- K9: GRU cell pointwise parts (matrix products go through ur_gemm_f32).
  * replaces: nn.GRU inside GRU.forward_user_emb unirec/model/sequential/gru.py:30 */

@@ -45,6 +45,20 @@ CASES = {
     'sasrec_bpr_nopos_padedges': dict(model='SASRec', n_items=157, n_users=29, embedding_size=64, hidden_size=64,
                                       n_layers=2, n_heads=4, inner_size=96, max_seq_len=11, loss_type='bpr',
                                       use_position_emb=0, hidden_act='gelu', K=3, B=8, init_std=0.2, edge=1),
+    # stock config/model/SASRec.yaml head count (n_heads 16 -> head dim 4 at d = 64)
+    'sasrec_h16_d64': dict(model='SASRec', n_items=181, n_users=23, embedding_size=64, hidden_size=64, n_layers=2, n_heads=16,
+                           inner_size=128, max_seq_len=12, loss_type='softmax', K=6, B=5, init_std=0.2),
+    # dropout > 0: the reference's nn.Dropout modules are replaced by explicit multipliers computed by oracle/philox.py (the
+    # generator the CUDA kernels implement), so loss / grads / trajectory are the reference's arithmetic on a known mask set
+    'sasrec_softmax_drop': dict(model='SASRec', n_items=211, n_users=37, embedding_size=32, hidden_size=32, n_layers=2, n_heads=2,
+                                inner_size=64, max_seq_len=8, loss_type='softmax', K=5, B=8, init_std=0.2, edge=1,
+                                hidden_dropout_prob=0.3, attn_dropout_prob=0.2, drop_step=5),
+    # the stock SASRec.yaml recipe: 16 heads (head dim 2 at d = 32), dropout 0.5 / 0.5, swish
+    'sasrec_stock_drop': dict(model='SASRec', n_items=157, n_users=29, embedding_size=32, hidden_size=32, n_layers=2, n_heads=16,
+                              inner_size=64, max_seq_len=10, loss_type='softmax', K=4, B=6, init_std=0.2,
+                              hidden_dropout_prob=0.5, attn_dropout_prob=0.5, drop_step=11),
+    'gru_bpr_drop': dict(model='GRU', n_items=123, n_users=19, embedding_size=32, hidden_size=64, max_seq_len=7, loss_type='bpr',
+                         K=5, B=6, init_std=0.3, dropout_prob=0.4, drop_step=3),
     'gru_bpr': dict(model='GRU', n_items=123, n_users=19, embedding_size=32, hidden_size=64,
                     max_seq_len=7, loss_type='bpr', K=5, B=6, init_std=0.3),
     'gru_softmax_h32': dict(model='GRU', n_items=99, n_users=19, embedding_size=32, hidden_size=32,
@@ -94,8 +108,36 @@ def make_batch(cfg, B, K, L, gen, edge=False):
     return dict(user_id=user_id, item_id=item_id, label=label, item_seq=item_seq, item_seq_len=lens)
 
 
+class InjectedDropout(torch.nn.Module):
+    """Stands in for one nn.Dropout of the reference model: multiplies by the explicit mask `store[key]`."""
+
+    def __init__(self, store, key):
+        super().__init__()
+        self.store, self.key = store, key
+
+    def forward(self, x):
+        return x * self.store[self.key].view(x.shape) if self.training else x
+
+
+def inject_dropout(model, name, store):
+    """Replace every nn.Dropout on the tower by an InjectedDropout reading `store` (keys of oracle/philox.py)."""
+    if name == 'SASRec':
+        model.dropout = InjectedDropout(store, 'input')                       # sasrec.py:69
+        for i, layer in enumerate(model.trm_encoder.layer):
+            layer.multi_head_attention.attn_dropout = InjectedDropout(store, 'attn.%d' % i)       # modules.py:307
+            layer.multi_head_attention.out_dropout = InjectedDropout(store, 'attn_out.%d' % i)    # modules.py:313
+            layer.feed_forward.dropout = InjectedDropout(store, 'ffn_out.%d' % i)                 # modules.py:352
+    elif name == 'GRU':
+        model.emb_dropout = InjectedDropout(store, 'input')                   # gru.py:29
+    else:
+        raise ValueError(name)
+    assert not any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in model.modules())
+
+
 def main():
     sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+    from oracle import philox
     from unirec.utils import argument_parser, general
     os.makedirs(OUT, exist_ok=True)
     saved_argv, sys.argv = sys.argv, sys.argv[:1]
@@ -106,6 +148,7 @@ def main():
         case = dict(case)
         B, K = case.pop('B'), case.pop('K')
         edge = bool(case.pop('edge', 0))
+        drop_step = case.pop('drop_step', None)
         args = dict(BASE)
         args.update(case)
         cfg = argument_parser.parse_arguments(args)
@@ -124,6 +167,18 @@ def main():
         out = {}
         for k, v in model.state_dict().items():
             out['param/' + k] = v.detach().numpy().copy()
+        store = {}
+
+        def set_masks(step):
+            if drop_step is None:
+                return
+            fn = philox.sasrec_masks if cfg['model'] == 'SASRec' else philox.gru_masks
+            store.clear()
+            store.update(fn(cfg, B, L, seed, step))
+
+        if drop_step is not None:
+            inject_dropout(model, cfg['model'], store)
+            set_masks(drop_step)
         loss, scores, user_emb, items_emb = model(**fwd_batch, return_loss_only=False)
         model.zero_grad()
         loss.backward()
@@ -139,7 +194,8 @@ def main():
         opt = torch.optim.Adam(model.parameters(), lr=float(cfg['learning_rate']),
                                weight_decay=float(cfg['weight_decay']))
         traj = []
-        for _ in range(3):
+        for it in range(3):
+            set_masks((drop_step or 0) + it)            # one mask set per training step
             l_ = model(**fwd_batch)[0]
             opt.zero_grad()
             l_.backward()
@@ -153,6 +209,8 @@ def main():
         keep = {k: v for k, v in cfg.items()
                 if isinstance(v, (int, float, str, bool)) and k not in ('exp_name', 'config_dir')}
         keep['K'], keep['B'] = K, B
+        if drop_step is not None:
+            keep['drop_seed'], keep['drop_step'] = seed, drop_step
         out['config_json'] = np.frombuffer(json.dumps(keep, sort_keys=True).encode(), dtype=np.uint8)
         path = os.path.join(OUT, name + '.npz')
         np.savez_compressed(path, **out)

@@ -125,8 +125,9 @@ def sasrec_attention_mask(item_seq, causal: bool, dtype):
     return (1.0 - key_ok) * -10000.0
 
 
-def multi_head_attention(x, mask, p: Dict[str, torch.Tensor], prefix: str, n_heads: int, eps: float):
-    """unirec/model/modules.py:284-316 (dropout = identity, the parity configuration)."""
+def multi_head_attention(x, mask, p: Dict[str, torch.Tensor], prefix: str, n_heads: int, eps: float, m_attn=None, m_out=None):
+    """unirec/model/modules.py:284-316.  m_attn [B,H,L,L] / m_out [B,L,D]: explicit multipliers standing in for
+    attn_dropout (:307) and out_dropout (:313); None = identity (eval mode / p = 0)."""
     B, L, D = x.shape
     dh = D // n_heads
 
@@ -138,20 +139,28 @@ def multi_head_attention(x, mask, p: Dict[str, torch.Tensor], prefix: str, n_hea
     v = split(linear(x, p[prefix + 'value.weight'], p[prefix + 'value.bias']))
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh) + mask
     a = torch.softmax(s, dim=-1)
+    if m_attn is not None:
+        a = a * m_attn
     ctx = torch.matmul(a, v).permute(0, 2, 1, 3).contiguous().view(B, L, D)
     h = linear(ctx, p[prefix + 'dense.weight'], p[prefix + 'dense.bias'])
+    if m_out is not None:
+        h = h * m_out
     return layer_norm(h + x, p[prefix + 'LayerNorm.weight'], p[prefix + 'LayerNorm.bias'], eps)
 
 
-def feed_forward(x, p, prefix, act: str, eps: float):
-    """unirec/model/modules.py:347-355."""
+def feed_forward(x, p, prefix, act: str, eps: float, m_out=None):
+    """unirec/model/modules.py:347-355 (m_out: multipliers standing in for the dropout at :352)."""
     h = activation(linear(x, p[prefix + 'dense_1.weight'], p[prefix + 'dense_1.bias']), act)
     h = linear(h, p[prefix + 'dense_2.weight'], p[prefix + 'dense_2.bias'])
+    if m_out is not None:
+        h = h * m_out
     return layer_norm(h + x, p[prefix + 'LayerNorm.weight'], p[prefix + 'LayerNorm.bias'], eps)
 
 
-def sasrec_user_emb(p, cfg, item_seq):
-    """unirec/model/sequential/sasrec.py:59-76 (+ recommender.py:136-137 for the gather)."""
+def sasrec_user_emb(p, cfg, item_seq, drop=None):
+    """unirec/model/sequential/sasrec.py:59-76 (+ recommender.py:136-137 for the gather).  drop: dict of explicit dropout
+    multipliers (oracle/philox.py:sasrec_masks) or None."""
+    drop = drop or {}
     eps = float(cfg['layer_norm_eps'])
     causal = bool(cfg.get('use_position_emb', True))
     x = gather_rows(p['item_embedding.weight'], item_seq)
@@ -159,21 +168,27 @@ def sasrec_user_emb(p, cfg, item_seq):
         L = item_seq.shape[1]
         x = x + p['position_embedding.weight'][:L][None]
     x = layer_norm(x, p['LayerNorm.weight'], p['LayerNorm.bias'], eps)
+    if drop.get('input') is not None:                      # sasrec.py:69
+        x = x * drop['input']
     mask = sasrec_attention_mask(item_seq, causal, x.dtype)
     for i in range(int(cfg['n_layers'])):
         pre = 'trm_encoder.layer.%d.' % i
-        x = multi_head_attention(x, mask, p, pre + 'multi_head_attention.', int(cfg['n_heads']), eps)
-        x = feed_forward(x, p, pre + 'feed_forward.', cfg['hidden_act'], eps)
+        x = multi_head_attention(x, mask, p, pre + 'multi_head_attention.', int(cfg['n_heads']), eps,
+                                 drop.get('attn.%d' % i), drop.get('attn_out.%d' % i))
+        x = feed_forward(x, p, pre + 'feed_forward.', cfg['hidden_act'], eps, drop.get('ffn_out.%d' % i))
     return x[:, -1, :]
 
 
 # --------------------------------------------------------------------------
 # a6: GRU tower
 # --------------------------------------------------------------------------
-def gru_user_emb(p, cfg, item_seq):
+def gru_user_emb(p, cfg, item_seq, drop=None):
     """unirec/model/sequential/gru.py:27-35.  nn.GRU(batch_first, 1 layer) restated from the PyTorch
-    definition: r,z,n gate order; n = tanh(W_in x + b_in + r*(W_hn h + b_hn)); h' = (1-z)*n + z*h."""
+    definition: r,z,n gate order; n = tanh(W_in x + b_in + r*(W_hn h + b_hn)); h' = (1-z)*n + z*h.
+    drop['input']: explicit multipliers standing in for emb_dropout (gru.py:29)."""
     x = gather_rows(p['item_embedding.weight'], item_seq)
+    if drop and drop.get('input') is not None:
+        x = x * drop['input']
     w_ih, w_hh = p['gru_layers.weight_ih_l0'], p['gru_layers.weight_hh_l0']
     b_ih, b_hh = p['gru_layers.bias_ih_l0'], p['gru_layers.bias_hh_l0']
     H = w_hh.shape[1]
@@ -219,11 +234,11 @@ def mf_user_emb(p, cfg, user_id):
 # --------------------------------------------------------------------------
 # a11: forward orchestration
 # --------------------------------------------------------------------------
-def forward_user_emb(model: str, p, cfg, user_id=None, item_seq=None, item_seq_len=None):
+def forward_user_emb(model: str, p, cfg, user_id=None, item_seq=None, item_seq_len=None, drop=None):
     if model == 'SASRec':
-        return sasrec_user_emb(p, cfg, item_seq)
+        return sasrec_user_emb(p, cfg, item_seq, drop)
     if model == 'GRU':
-        return gru_user_emb(p, cfg, item_seq)
+        return gru_user_emb(p, cfg, item_seq, drop)
     if model == 'AvgHist':
         return avghist_user_emb(p, cfg, item_seq, item_seq_len)
     if model == 'SVDPlusPlus':
@@ -234,11 +249,11 @@ def forward_user_emb(model: str, p, cfg, user_id=None, item_seq=None, item_seq_l
 
 
 def forward(model: str, p, cfg, user_id=None, item_id=None, label=None, item_seq=None,
-            item_seq_len=None, reduction=True):
+            item_seq_len=None, reduction=True, drop=None):
     """BaseRecommender.forward (training branch).  unirec/model/base/recommender.py:46-64.
     Returns (loss, scores, user_emb, items_emb)."""
     items_emb = gather_rows(p['item_embedding.weight'], item_id)   # src table for AvgHist/SVD++ too
-    user_emb = forward_user_emb(model, p, cfg, user_id, item_seq, item_seq_len)
+    user_emb = forward_user_emb(model, p, cfg, user_id, item_seq, item_seq_len, drop)
     scores = inner_product_scores(user_emb, items_emb)
     scores = predict_layer(scores, user_id, item_id,
                            p.get('user_bias') if cfg.get('has_user_bias') else None,
@@ -265,11 +280,11 @@ def tie_aliases(model, cfg, p):
 PADDING_TABLES = ('item_embedding.weight', 'item_dst_embedding.weight', 'user_embedding.weight')
 
 
-def loss_and_grads(model, p, cfg, batch):
+def loss_and_grads(model, p, cfg, batch, drop=None):
     """Autograd backward of `forward`, with the `padding_idx=0` rule of nn.Embedding: the gradient
     row 0 of every padded table is zero (reco_abc.py:167-170)."""
     leaves = tie_aliases(model, cfg, {k: v.detach().clone().requires_grad_(True) for k, v in p.items()})
-    loss, scores, user_emb, _ = forward(model, leaves, cfg, **batch)
+    loss, scores, user_emb, _ = forward(model, leaves, cfg, drop=drop, **batch)
     loss.backward()
     grads = {}
     for k, v in leaves.items():
@@ -341,10 +356,10 @@ class LazyRowAdam(DenseAdam):
             p[sl] = ps - (self.lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + self.eps)
 
 
-def train_step(model, p, cfg, batch, opt: DenseAdam):
+def train_step(model, p, cfg, batch, opt: DenseAdam, drop=None):
     """One iteration of Trainer.fit's inner loop: forward, backward, optimizer step.
     unirec/facility/trainer.py:340-349.  Mutates `p` in place; returns the loss."""
-    loss, _, _, grads = loss_and_grads(model, p, cfg, batch)
+    loss, _, _, grads = loss_and_grads(model, p, cfg, batch, drop=drop)
     if torch.isnan(loss):          # trainer.py:344-352: a NaN loss skips the update
         return loss
     opt.step(p, grads)

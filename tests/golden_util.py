@@ -25,6 +25,22 @@ class Golden:
         self.user_emb = torch.from_numpy(z['user_emb'])
         self.traj_loss = z['traj_loss']
         self.model = self.cfg['model']
+        # dropout fixtures: the reference ran with explicit masks of (drop_seed, drop_step + iteration), see oracle/make_golden.py
+        self.drop_seed, self.drop_step = self.cfg.get('drop_seed'), self.cfg.get('drop_step')
+
+    def drop_masks(self, it=0):
+        """Explicit dropout multipliers of training iteration `it` (None for the dropout-free fixtures)."""
+        if self.drop_step is None:
+            return None
+        from oracle import philox
+        B, L = self.batch['item_seq'].shape
+        fn = philox.sasrec_masks if self.model == 'SASRec' else philox.gru_masks
+        return fn(self.cfg, B, L, self.drop_seed, self.drop_step + it)
+
+    def arm(self, model, it=0):
+        """Make the next training forward of a unirec_b200 model draw this fixture's mask set."""
+        if self.drop_step is not None:
+            model._engine.set_dropout_state(self.drop_seed, self.drop_step + it)
 
     def fwd_batch(self):
         if self.model == 'MF':

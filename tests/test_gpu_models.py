@@ -23,7 +23,7 @@ def _traj_tol(name):
     """3-step Adam trajectories: 2e-3.  The pad-edge fixtures hold an empty-history sample whose attention logits all sit at
     s - 10000, i.e. on the 1e-3 grid of fp32 -- the reference's own output for it is quantised, summation-order differences flip
     grid points and Adam turns them into fractions of lr (the CPU oracle itself is 6e-4 off the reference there)."""
-    return 6e-3 if name.endswith('padedges') else 2e-3
+    return 6e-3 if (name.endswith('padedges') or name == 'sasrec_softmax_drop') else 2e-3
 
 
 def to_dev(batch):
@@ -35,16 +35,22 @@ def test_forward_matches_reference(name):
     g = Golden(name)
     model, _ = cuda_model(g)
     model.train()
+    g.arm(model)            # dropout fixtures: draw the mask set the reference ran with (no-op otherwise)
     loss, scores, user_emb, items_emb = model(**to_dev(g.fwd_batch()), return_loss_only=False)
     assert abs(float(loss) - float(g.loss)) <= TOL * abs(float(g.loss))
     assert rel_err(scores.cpu(), g.scores) < TOL
     assert rel_err(user_emb.cpu(), g.user_emb) < TOL
     assert torch.equal(items_emb.cpu(), O.gather_rows(g.params['item_embedding.weight'], g.batch['item_id']))   # bit-exact
+    g.arm(model)
     loss_vec = model(**to_dev(g.fwd_batch()), reduction=False)[0]
     assert rel_err(loss_vec.detach().cpu(), g.loss_vec) < TOL
     model.eval()
     none, s2, u2, _ = model(**to_dev(g.fwd_batch()))
-    assert none is None and rel_err(s2.cpu(), g.scores) < TOL and rel_err(u2.cpu(), g.user_emb) < TOL
+    if g.drop_step is None:
+        assert none is None and rel_err(s2.cpu(), g.scores) < TOL and rel_err(u2.cpu(), g.user_emb) < TOL
+    else:       # eval mode = dropout off: the oracle without masks
+        _, so, uo, _ = O.forward(g.model, g.params, g.cfg, **g.fwd_batch())
+        assert none is None and rel_err(s2.cpu(), so) < TOL and rel_err(u2.cpu(), uo) < TOL
 
 
 @pytest.mark.parametrize('name', CASES)
@@ -53,6 +59,7 @@ def test_autograd_grads_match_reference_dense_mode(name):
     g = Golden(name)
     model, _ = cuda_model(g, table_update='dense')
     model.train()
+    g.arm(model)
     loss = model(**to_dev(g.fwd_batch()))[0]
     loss.backward()
     scale = max(float(v.abs().max()) for v in g.grads.values())
@@ -73,6 +80,7 @@ def test_dense_mode_trajectory_matches_reference_adam(name):
     model._ur_fast_grads = True
     opt = FusedOptimizer(model, 'adam', lr=float(cfg['learning_rate']), weight_decay=float(cfg['weight_decay']))
     batch = to_dev(g.fwd_batch())
+    g.arm(model)            # the step counter then advances by one per training forward, like the fixture's mask sets
     for ref_loss in g.traj_loss:
         loss = model(**batch)[0]
         opt.zero_grad()
@@ -108,12 +116,13 @@ def test_sparse_mode_trajectory_matches_lazy_oracle(name):
         touched['user_embedding.weight'] = [b['user_id']]
     touched = {k: torch.cat(v) for k, v in touched.items()}
     batch = to_dev(g.fwd_batch())
-    for _ in range(3):
+    g.arm(model)
+    for it in range(3):
         loss = model(**batch)[0]
         opt.zero_grad()
         loss.backward()
         opt.step()
-        ref_loss, _, _, grads = O.loss_and_grads(g.model, p, g.cfg, g.fwd_batch())
+        ref_loss, _, _, grads = O.loss_and_grads(g.model, p, g.cfg, g.fwd_batch(), drop=g.drop_masks(it))
         oopt.step(p, grads, touched)
         assert abs(float(loss) - float(ref_loss)) <= TOL * abs(float(ref_loss))
     sd = model.state_dict()
@@ -208,7 +217,8 @@ def test_trainer_fit_loop_and_checkpoint(tmp_path):
     assert set(model2.state_dict()) == set(model.state_dict())
 
 
-@pytest.mark.parametrize('name', ['sasrec_softmax', 'sasrec_softmax_padedges', 'sasrec_bpr_nopos_padedges', 'sasrec_softmax_d128'])
+@pytest.mark.parametrize('name', ['sasrec_softmax', 'sasrec_softmax_padedges', 'sasrec_bpr_nopos_padedges', 'sasrec_softmax_d128',
+                                  'sasrec_softmax_drop', 'sasrec_stock_drop', 'sasrec_h16_d64'])
 @pytest.mark.parametrize('pack,trim', [(0, 1), (1, 0), (0, 0)])
 def test_sasrec_packing_and_trimming_do_not_change_results(name, pack, trim):
     """pack_sequences / trim_last_layer only remove dead work: every combination must reproduce the reference goldens (the default
@@ -216,6 +226,7 @@ def test_sasrec_packing_and_trimming_do_not_change_results(name, pack, trim):
     g = Golden(name)
     model, _ = cuda_model(g, table_update='dense', pack_sequences=pack, trim_last_layer=trim)
     model.train()
+    g.arm(model)            # dropout masks are indexed by original positions: packing / trimming must not move them
     loss, scores, user_emb, _ = model(**to_dev(g.fwd_batch()), return_loss_only=False)
     assert abs(float(loss) - float(g.loss)) <= TOL * abs(float(g.loss))
     assert rel_err(scores.cpu(), g.scores) < TOL and rel_err(user_emb.cpu(), g.user_emb) < TOL

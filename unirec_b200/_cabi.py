@@ -18,10 +18,13 @@ SIGNATURES = {
     'ur_gather_rows_f32': 'plipilpp',
     'ur_scatter_add_rows_f32': 'plipilplpllp',
     'ur_pool_sum_fwd_f32': 'piplipfppppp',
-    'ur_seq_prep_ln_fwd_f32': 'ppppfpliippp' + 'pp' + 'pi' + 'p',
-    'ur_seq_prep_ln_bwd_f32': 'pppplii' + 'ppp' + 'pppp' + 'p' + 'pi' + 'p',
-    'ur_add_ln_fwd_f32': 'plplppflipl' + 'pp' + 'p' + 'p',
-    'ur_add_ln_bwd_f32': 'plppp' + 'pl' + 'pl' + 'li' + 'pl' + 'ppp' + 'p' + 'p',
+    'ur_seq_prep_ln_fwd_f32': 'ppppfpliippp' + 'pp' + 'pi' + 'pfi' + 'p',
+    'ur_seq_prep_ln_bwd_f32': 'pppplii' + 'ppp' + 'pppp' + 'p' + 'pi' + 'pfi' + 'p',
+    'ur_add_ln_fwd_f32': 'plplppflipl' + 'pp' + 'p' + 'pfipll' + 'p',
+    'ur_add_ln_bwd_f32': 'plppp' + 'pl' + 'pl' + 'li' + 'pl' + 'ppp' + 'p' + 'pl' + 'pfipll' + 'p',
+    'ur_dropout_rows_f32': 'pllipllppfi' + 'p',
+    'ur_dropout_mask_f32': 'plipllpfii' + 'p',
+    'ur_rng_advance': 'pp',
     'ur_gemm_f32': 'iilllplplplpipliip',
     'ur_gemm_simt_f32': 'iilllplplplpiplip',
     'ur_gemm_tc_f32': 'iilllplplplpipliip',
@@ -32,8 +35,8 @@ SIGNATURES = {
     'ur_transpose_f32': 'pllpp',
     'ur_act_bwd_f32': 'pplip',
     'ur_colsum_accum_f32': 'plllp' + 'p' + 'p',
-    'ur_attn_fwd_f32': 'ppliiiiipp' + 'ppp' + 'p',
-    'ur_attn_bwd_f32': 'ppliiiii' + 'pppp' + 'pppp' + 'p',
+    'ur_attn_fwd_f32': 'ppliiiiipp' + 'ppp' + 'pfi' + 'p',
+    'ur_attn_bwd_f32': 'ppliiiii' + 'pppp' + 'pppp' + 'pfi' + 'p',
     'ur_gru_gate_fwd_f32': 'plppppli' + 'p',
     'ur_gru_gate_bwd_f32': 'pppplppli' + 'p',
     'ur_score_loss_fwd_bwd_f32': 'pipplipppp' + 'ffipf' + 'pppp' + 'p',

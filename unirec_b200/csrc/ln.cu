@@ -2,6 +2,7 @@
 //   seq_prep_ln: Y = LN(E[item_seq] + P[0..L-1])      unirec/model/sequential/sasrec.py:60-68
 //   add_ln:      Y = LN(X + R)  (post-LN residual)    unirec/model/modules.py:313-314, 352-353
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace ur {
 
@@ -32,7 +33,8 @@ __device__ __forceinline__ void row_stats(const RowRegs<MAXV>& x, int d4, int la
 template <int MAXV>
 __device__ __forceinline__ void ln_apply_store(const RowRegs<MAXV>& x, int d4, int lane, float mean, float rstd,
                                                const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                                               float4* __restrict__ y) {
+                                               float4* __restrict__ y, const DropCfg& dc = DropCfg{0, 0, 0, 0, 0, 1.f, false},
+                                               unsigned long long drop_row = 0) {
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         int c = lane + 32 * i;
@@ -42,6 +44,7 @@ __device__ __forceinline__ void ln_apply_store(const RowRegs<MAXV>& x, int d4, i
             o.y = (x.v[i].y - mean) * rstd * g.y + b.y;
             o.z = (x.v[i].z - mean) * rstd * g.z + b.z;
             o.w = (x.v[i].w - mean) * rstd * g.w + b.w;
+            if (dc.on) o = f4_mul(o, drop_mask4(dc, drop_row * (unsigned long long)d4 + c));   // dropout(LN(.)), sasrec.py:68-69
             y[c] = o;
         }
     }
@@ -55,10 +58,12 @@ __global__ void __launch_bounds__(256) seq_prep_ln_fwd_kernel(const float4* __re
                                                               float4* __restrict__ Y, float* __restrict__ mean_out,
                                                               float* __restrict__ rstd_out, const int32_t* __restrict__ tok_src,
                                                               const int32_t* __restrict__ n_tok_dev,
-                                                              const long long* __restrict__ shard_ptrs, int shard_world) {
+                                                              const long long* __restrict__ shard_ptrs, int shard_world,
+                                                              const long long* __restrict__ rng, float drop_p, int drop_site) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const DropCfg dc = drop_cfg(rng, drop_p, drop_site);
     // packed mode (csrc/pack.cu): output row t holds position tok_src[t]; rows [n_tok, roundup32(n_tok)) are written as zeros
     // (the token-reduction GEMMs consume whole 32-row blocks)
     const int64_t n_live = n_tok_dev ? min((int64_t)*n_tok_dev, rows) : rows;
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(256) seq_prep_ln_fwd_kernel(const float4* __re
         }
         float mean, rstd;
         row_stats<MAXV>(x, d4, lane, eps, mean, rstd);
-        ln_apply_store<MAXV>(x, d4, lane, mean, rstd, gamma, beta, Y + r * d4);
+        ln_apply_store<MAXV>(x, d4, lane, mean, rstd, gamma, beta, Y + r * d4, dc, (unsigned long long)src);
         if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
     }
 }
@@ -167,10 +172,12 @@ __global__ void __launch_bounds__(256) seq_prep_ln_bwd_kernel(const float4* __re
                                                               float4* __restrict__ dX, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ dpos,
                                                               const int32_t* __restrict__ tok_inv,
-                                                              const long long* __restrict__ shard_ptrs, int shard_world) {
+                                                              const long long* __restrict__ shard_ptrs, int shard_world,
+                                                              const long long* __restrict__ rng, float drop_p, int drop_site) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31;
     const int l = blockIdx.y;
+    const DropCfg dc = drop_cfg(rng, drop_p, drop_site);
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     RowRegs<MAXV> dgam, dbet, dp;
@@ -192,6 +199,7 @@ __global__ void __launch_bounds__(256) seq_prep_ln_bwd_kernel(const float4* __re
                 x.v[i] = ldg_stream(trow + c);
                 if (pos) x.v[i] = f4_add(x.v[i], __ldg(pos + (int64_t)l * d4 + c));
                 dy.v[i] = dY[t * d4 + c];
+                if (dc.on) dy.v[i] = f4_mul(dy.v[i], drop_mask4(dc, (unsigned long long)r * d4 + c));   // the forward's mask of position r
             }
         }
         ln_bwd_row<MAXV>(x, dy, d4, lane, mean_in[t], rstd_in[t], gamma, dx, dgam, dbet);
@@ -210,13 +218,17 @@ __global__ void __launch_bounds__(256) seq_prep_ln_bwd_kernel(const float4* __re
 }
 
 // ------------------------------------------------------------------ residual add + LN
-// Z = X + R is written back over X (kept for backward); Y = LN(Z).
+// Z = dropout(X) + R is written back over X (kept for backward); Y = LN(Z).  Dropout (modules.py:313, :352) is indexed by the
+// ORIGINAL position of the row: row_pos[r] (packed token map) or r * pos_mul + pos_add (compact last-layer rows).
 template <int MAXV>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(float* __restrict__ X, int64_t ldx, const float* __restrict__ R, int64_t ldr,
                                                          const float4* __restrict__ gamma, const float4* __restrict__ beta, float eps,
                                                          int64_t rows, int d4, float* __restrict__ Y, int64_t ldy,
                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                         const int32_t* __restrict__ rows_dev) {
+                                                         const int32_t* __restrict__ rows_dev, const long long* __restrict__ rng,
+                                                         float drop_p, int drop_site, const int32_t* __restrict__ row_pos,
+                                                         int64_t pos_mul, int64_t pos_add) {
+    const DropCfg dc = drop_cfg(rng, drop_p, drop_site);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -236,12 +248,15 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(float* __restrict__ X, 
         float4* xr = reinterpret_cast<float4*>(X + r * ldx);
         const float4* rr = R ? reinterpret_cast<const float4*>(R + r * ldr) : nullptr;
         RowRegs<MAXV> x;
+        const unsigned long long prow = dc.on ? (unsigned long long)(row_pos ? (int64_t)__ldg(row_pos + r) : r * pos_mul + pos_add) : 0ull;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             int c = lane + 32 * i;
             if (c < d4) {
                 x.v[i] = xr[c];
-                if (rr) { x.v[i] = f4_add(x.v[i], rr[c]); xr[c] = x.v[i]; }
+                if (dc.on) x.v[i] = f4_mul(x.v[i], drop_mask4(dc, prow * d4 + c));
+                if (rr) x.v[i] = f4_add(x.v[i], rr[c]);
+                if (rr || dc.on) xr[c] = x.v[i];
             }
         }
         float mean, rstd;
@@ -251,15 +266,21 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(float* __restrict__ X, 
     }
 }
 
-// dZ = LN'(Z) dY (may alias dY); optional dZ += dExtra (gradient arriving through the residual branch of the NEXT op)
+// dZ = LN'(Z) dY (may alias dY); optional dZ += dExtra (gradient arriving through the residual branch of the NEXT op).
+// With dropout on the linear branch (Z = dropout(X) + R): dZdrop = dZ * mask is the gradient of X (feeds the weight / input
+// gradients of the producing linear layer and its bias gradient dzsum); dZ itself flows down the residual branch.
 template <int MAXV>
 __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict__ Z, int64_t ldz, const float4* __restrict__ gamma,
                                                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                          const float* dY, int64_t lddy, const float* __restrict__ dExtra, int64_t ldde,
                                                          int64_t rows, int d4, float* dZ, int64_t lddz,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                         float* __restrict__ dzsum, const int32_t* __restrict__ rows_dev) {
+                                                         float* __restrict__ dzsum, const int32_t* __restrict__ rows_dev,
+                                                         float* __restrict__ dZdrop, int64_t lddzd, const long long* __restrict__ rng,
+                                                         float drop_p, int drop_site, const int32_t* __restrict__ row_pos,
+                                                         int64_t pos_mul, int64_t pos_add) {
     extern __shared__ float smem[];
+    const DropCfg dc = drop_cfg(dZdrop ? rng : nullptr, drop_p, drop_site);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -270,10 +291,14 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
     for (int64_t r = warp0; r < n_pad; r += nwarps) {
         if (r >= n_live) {                         // zero tail: dZ is the token-reduction operand of the weight-gradient GEMM
             float4* dzt = reinterpret_cast<float4*>(dZ + r * lddz);
+            float4* dzdt = dc.on ? reinterpret_cast<float4*>(dZdrop + r * lddzd) : nullptr;
 #pragma unroll
             for (int i = 0; i < MAXV; ++i) {
                 int c = lane + 32 * i;
-                if (c < d4) dzt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < d4) {
+                    dzt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (dzdt) dzdt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             continue;
         }
@@ -292,10 +317,17 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
         }
         ln_bwd_row<MAXV>(x, dy, d4, lane, mean_in[r], rstd_in[r], gamma, dx, dgam, dbet);
         float4* dzr = reinterpret_cast<float4*>(dZ + r * lddz);
+        float4* dzdr = dc.on ? reinterpret_cast<float4*>(dZdrop + r * lddzd) : nullptr;
+        const unsigned long long prow = dc.on ? (unsigned long long)(row_pos ? (int64_t)__ldg(row_pos + r) : r * pos_mul + pos_add) : 0ull;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             int c = lane + 32 * i;
-            if (c < d4) { dzr[c] = dx.v[i]; dzs.v[i] = f4_add(dzs.v[i], dx.v[i]); }
+            if (c < d4) {
+                dzr[c] = dx.v[i];
+                float4 gx = dx.v[i];
+                if (dc.on) { gx = f4_mul(gx, drop_mask4(dc, prow * d4 + c)); dzdr[c] = gx; }
+                dzs.v[i] = f4_add(dzs.v[i], gx);
+            }
         }
     }
     block_accumulate<MAXV>(dgam, d4, dgamma, smem);
@@ -322,8 +354,10 @@ extern "C" {
 
 int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* gamma, const float* beta, float eps,
                            const int32_t* item_seq, int64_t B, int L, int d, float* Y, float* mean, float* rstd,
-                           const int32_t* tok_src, const int32_t* n_tok_dev, const void* shard_ptrs, int shard_world, void* stream) {
+                           const int32_t* tok_src, const int32_t* n_tok_dev, const void* shard_ptrs, int shard_world,
+                           const int64_t* rng, float drop_p, int drop_site, void* stream) {
     if (shard_ptrs && shard_world < 1) return UR_ERR_BAD_ARG;
+    if (drop_p < 0.f || drop_p >= 1.f) return UR_ERR_BAD_ARG;
     if (d <= 0 || (d & 3)) return UR_ERR_BAD_ARG;
     const int64_t rows = B * L;
     if (rows == 0) return UR_OK;
@@ -332,7 +366,7 @@ int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* ga
 #define CALL(MV)                                                                                                    \
     ur::seq_prep_ln_fwd_kernel<MV><<<ur::ln_grid(rows), 256, 0, st>>>(                                              \
         (const float4*)table, (const float4*)pos, (const float4*)gamma, (const float4*)beta, eps, item_seq, rows, L, d4, \
-        (float4*)Y, mean, rstd, tok_src, n_tok_dev, (const long long*)shard_ptrs, shard_world);
+        (float4*)Y, mean, rstd, tok_src, n_tok_dev, (const long long*)shard_ptrs, shard_world, (const long long*)rng, drop_p, drop_site);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();
@@ -340,8 +374,10 @@ int ur_seq_prep_ln_fwd_f32(const float* table, const float* pos, const float* ga
 
 int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* gamma, const int32_t* item_seq, int64_t B, int L,
                            int d, const float* mean, const float* rstd, const float* dY, float* dX, float* dgamma, float* dbeta,
-                           float* dpos, const int32_t* tok_inv, const void* shard_ptrs, int shard_world, void* stream) {
+                           float* dpos, const int32_t* tok_inv, const void* shard_ptrs, int shard_world, const int64_t* rng,
+                           float drop_p, int drop_site, void* stream) {
     if (shard_ptrs && shard_world < 1) return UR_ERR_BAD_ARG;
+    if (drop_p < 0.f || drop_p >= 1.f) return UR_ERR_BAD_ARG;
     if (d <= 0 || (d & 3)) return UR_ERR_BAD_ARG;
     if (B * L == 0) return UR_OK;
     const int d4 = d / 4;
@@ -353,21 +389,26 @@ int ur_seq_prep_ln_bwd_f32(const float* table, const float* pos, const float* ga
 #define CALL(MV)                                                                                               \
     ur::seq_prep_ln_bwd_kernel<MV><<<grid, 256, d * sizeof(float), st>>>(                                      \
         (const float4*)table, (const float4*)pos, (const float4*)gamma, item_seq, B, L, d4, mean, rstd,        \
-        (const float4*)dY, (float4*)dX, dgamma, dbeta, dpos, tok_inv, (const long long*)shard_ptrs, shard_world);
+        (const float4*)dY, (float4*)dX, dgamma, dbeta, dpos, tok_inv, (const long long*)shard_ptrs, shard_world,    \
+        (const long long*)rng, drop_p, drop_site);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();
 }
 
 int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R, int64_t ldr, const float* gamma, const float* beta, float eps,
-                      int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd, const int32_t* rows_dev, void* stream) {
+                      int64_t rows, int d, float* Y, int64_t ldy, float* mean, float* rstd, const int32_t* rows_dev,
+                      const int64_t* rng, float drop_p, int drop_site, const int32_t* row_pos, int64_t pos_mul, int64_t pos_add,
+                      void* stream) {
     if (d <= 0 || (d & 3) || (ldx & 3) || (ldr & 3) || (ldy & 3)) return UR_ERR_BAD_ARG;
+    if (drop_p < 0.f || drop_p >= 1.f) return UR_ERR_BAD_ARG;
     if (rows == 0) return UR_OK;
     const int d4 = d / 4;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(MV)                                                                                                      \
     ur::add_ln_fwd_kernel<MV><<<ur::ln_grid(rows), 256, 0, st>>>(X, ldx, R, ldr, (const float4*)gamma, (const float4*)beta, \
-                                                                 eps, rows, d4, Y, ldy, mean, rstd, rows_dev);
+                                                                 eps, rows, d4, Y, ldy, mean, rstd, rows_dev,               \
+                                                                 (const long long*)rng, drop_p, drop_site, row_pos, pos_mul, pos_add);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();
@@ -375,8 +416,11 @@ int ur_add_ln_fwd_f32(float* X, int64_t ldx, const float* R, int64_t ldr, const 
 
 int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const float* mean, const float* rstd, const float* dY,
                       int64_t lddy, const float* dExtra, int64_t ldde, int64_t rows, int d, float* dZ, int64_t lddz,
-                      float* dgamma, float* dbeta, float* dzsum, const int32_t* rows_dev, void* stream) {
-    if (d <= 0 || (d & 3) || (ldz & 3) || (lddy & 3) || (ldde & 3) || (lddz & 3)) return UR_ERR_BAD_ARG;
+                      float* dgamma, float* dbeta, float* dzsum, const int32_t* rows_dev, float* dZdrop, int64_t lddzd,
+                      const int64_t* rng, float drop_p, int drop_site, const int32_t* row_pos, int64_t pos_mul, int64_t pos_add,
+                      void* stream) {
+    if (d <= 0 || (d & 3) || (ldz & 3) || (lddy & 3) || (ldde & 3) || (lddz & 3) || (lddzd & 3)) return UR_ERR_BAD_ARG;
+    if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && rng != nullptr && dZdrop == nullptr)) return UR_ERR_BAD_ARG;
     if (rows == 0) return UR_OK;
     const int d4 = d / 4;
     cudaStream_t st = (cudaStream_t)stream;
@@ -384,7 +428,9 @@ int ur_add_ln_bwd_f32(const float* Z, int64_t ldz, const float* gamma, const flo
     if (grid > ur::kNumSMs * 2) grid = ur::kNumSMs * 2;   // fewer CTAs -> fewer column atomics
 #define CALL(MV)                                                                                                    \
     ur::add_ln_bwd_kernel<MV><<<grid, 256, d * sizeof(float), st>>>(Z, ldz, (const float4*)gamma, mean, rstd, dY, lddy, \
-                                                                    dExtra, ldde, rows, d4, dZ, lddz, dgamma, dbeta, dzsum, rows_dev);
+                                                                    dExtra, ldde, rows, d4, dZ, lddz, dgamma, dbeta, dzsum, rows_dev, \
+                                                                    dZdrop, lddzd, (const long long*)rng, drop_p, drop_site,    \
+                                                                    row_pos, pos_mul, pos_add);
     UR_LN_DISPATCH(d4, CALL)
 #undef CALL
     UR_RETURN_LAST_ERROR();

@@ -193,9 +193,18 @@ class SASRecTower:
         self.dh = self.d // self.H
         self.trim_last = bool(int(cfg.get('trim_last_layer', 1)))    # 0: compute the dead rows of the last layer too (A/B testing)
         self.packed = bool(int(cfg.get('pack_sequences', 1)))        # 0: keep every position (identity token map)
-        if float(cfg.get('hidden_dropout_prob', 0) or 0) > 0 or float(cfg.get('attn_dropout_prob', 0) or 0) > 0:
-            raise ValueError('unirec_b200: dropout > 0 is not implemented in the fused encoder yet; set '
-                             'hidden_dropout_prob=0 and attn_dropout_prob=0 (ignoring it silently would change training)')
+        # nn.Dropout sites of the reference (sasrec.py:69; modules.py:307,313,352), regenerated by counter in the backward kernels
+        self.p_hidden = float(cfg.get('hidden_dropout_prob', 0) or 0)
+        self.p_attn = float(cfg.get('attn_dropout_prob', 0) or 0)
+        for p_ in (self.p_hidden, self.p_attn):
+            if not 0.0 <= p_ < 1.0:
+                raise ValueError('dropout probabilities must lie in [0, 1), got %r' % (p_,))
+
+    # dropout site ids: 0 = input; layer i: 1+3i attention probabilities, 2+3i attention output, 3+3i FFN output
+    def _drop(self, site, p, row_pos=None, pos_mul=1, pos_add=0):
+        if p <= 0.0 or not self.eng.model.training:
+            return None
+        return ops.Drop(self.eng.rng, p, site, row_pos, pos_mul, pos_add)
 
     @staticmethod
     def flat_order(model):
@@ -236,8 +245,9 @@ class SASRecTower:
         pos = fp.p('position_embedding.weight') if self.causal else None
         x = ws.get('x0', (T, d))
         self.mean0, self.rstd0 = ws.get('mean0', (T,)), ws.get('rstd0', (T,))
+        self.drop0 = self._drop(0, self.p_hidden)
         ops.seq_prep_ln_fwd(table, pos, fp.p('LayerNorm.weight'), fp.p('LayerNorm.bias'), self.eps, index, x,
-                            self.mean0, self.rstd0, tok_src=pk['tok_src'], n_tok=pk['n'], shards=eng.seq_shards)
+                            self.mean0, self.rstd0, tok_src=pk['tok_src'], n_tok=pk['n'], shards=eng.seq_shards, drop=self.drop0)
         self.saved = []
         self.item_seq, self.pk = item_seq, pk
         user = ws.get('user_emb', (B, d))
@@ -264,12 +274,15 @@ class SASRecTower:
         qkv = ws.get('qkv' + tag, (T, 3 * d))
         ops.gemm(x, wqkv, qkv, T, 3 * d, d, transB=True, bias=bqkv, precision=prec, rows_dev=n)
         ctx, lse = ws.get('ctx' + tag, (T, d)), ws.get('lse' + tag, (B, H, L))
-        ops.attn_fwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, offs=pk['offs'], tok_src=pk['tok_src'])
+        drops = (self._drop(1 + 3 * i, self.p_attn), self._drop(2 + 3 * i, self.p_hidden, pk['tok_src']),
+                 self._drop(3 + 3 * i, self.p_hidden, pk['tok_src']))
+        ops.attn_fwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, offs=pk['offs'], tok_src=pk['tok_src'], drop=drops[0])
         z1 = ws.get('z1' + tag, (T, d))
         ops.gemm(ctx, fp.p(a + 'dense.weight'), z1, T, d, d, transB=True, bias=fp.p(a + 'dense.bias'), precision=prec, rows_dev=n)
         x1 = ws.get('x1' + tag, (T, d))
         m1, r1 = ws.get('m1' + tag, (T,)), ws.get('r1' + tag, (T,))
-        ops.add_ln_fwd(z1, x, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1, rows_dev=n)
+        ops.add_ln_fwd(z1, x, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1, rows_dev=n,
+                       drop=drops[1])
         hpre, hact = ws.get('hpre' + tag, (T, I)), ws.get('hact' + tag, (T, I))
         ops.gemm(x1, fp.p(f + 'dense_1.weight'), hact, T, I, d, transB=True, bias=fp.p(f + 'dense_1.bias'), act=self.act,
                  preact=hpre, precision=prec, rows_dev=n)
@@ -278,8 +291,9 @@ class SASRecTower:
                  rows_dev=n)
         x2 = ws.get('x2' + tag, (T, d))
         m2, r2 = ws.get('m2' + tag, (T,)), ws.get('r2' + tag, (T,))
-        ops.add_ln_fwd(z2, x1, fp.p(f + 'LayerNorm.weight'), fp.p(f + 'LayerNorm.bias'), self.eps, x2, m2, r2, rows_dev=n)
-        return ('full', x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, x2)
+        ops.add_ln_fwd(z2, x1, fp.p(f + 'LayerNorm.weight'), fp.p(f + 'LayerNorm.bias'), self.eps, x2, m2, r2, rows_dev=n,
+                       drop=drops[2])
+        return ('full', x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, x2, drops)
 
     def _layer_fwd_last(self, i, x, item_seq, pk, tag, user):
         """Last encoder layer: only position L-1 of its output reaches the scorer (sasrec.py:74-75), so everything after the
@@ -298,20 +312,25 @@ class SASRecTower:
         ql = ws.get('ql' + tag, (B, d))
         ops.gemm(xl, wqkv[:d * d], ql, B, d, d, transB=True, bias=bqkv[:d], precision=prec)
         ctx, lse = ws.get('ctxl' + tag, (B, d)), ws.get('lse' + tag, (B, H, L))
+        # compact rows: row b is position (b, L-1)
+        drops = (self._drop(1 + 3 * i, self.p_attn), self._drop(2 + 3 * i, self.p_hidden, None, L, L - 1),
+                 self._drop(3 + 3 * i, self.p_hidden, None, L, L - 1))
         ops.attn_fwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, q_only_last=True, offs=pk['offs'],
-                     tok_src=pk['tok_src'], q_last=ql)
+                     tok_src=pk['tok_src'], q_last=ql, drop=drops[0])
         z1 = ws.get('z1l' + tag, (B, d))
         ops.gemm(ctx, fp.p(a + 'dense.weight'), z1, B, d, d, transB=True, bias=fp.p(a + 'dense.bias'), precision=prec)
         x1 = ws.get('x1l' + tag, (B, d))
         m1, r1 = ws.get('m1l' + tag, (B,)), ws.get('r1l' + tag, (B,))
-        ops.add_ln_fwd(z1, xl, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1, rows=B, d=d)
+        ops.add_ln_fwd(z1, xl, fp.p(a + 'LayerNorm.weight'), fp.p(a + 'LayerNorm.bias'), self.eps, x1, m1, r1, rows=B, d=d,
+                       drop=drops[1])
         hpre, hact = ws.get('hprel' + tag, (B, I)), ws.get('hactl' + tag, (B, I))
         _lin_fwd(x1, B, d, fp.p(f + 'dense_1.weight'), fp.p(f + 'dense_1.bias'), I, hact, act=self.act, preact=hpre, prec=prec)
         z2 = ws.get('z2l' + tag, (B, d))
         _lin_fwd(hact, B, I, fp.p(f + 'dense_2.weight'), fp.p(f + 'dense_2.bias'), d, z2, prec=prec)
         m2, r2 = ws.get('m2l' + tag, (B,)), ws.get('r2l' + tag, (B,))
-        ops.add_ln_fwd(z2, x1, fp.p(f + 'LayerNorm.weight'), fp.p(f + 'LayerNorm.bias'), self.eps, user, m2, r2, rows=B, d=d)
-        return ('last', x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, xl, ql, user)
+        ops.add_ln_fwd(z2, x1, fp.p(f + 'LayerNorm.weight'), fp.p(f + 'LayerNorm.bias'), self.eps, user, m2, r2, rows=B, d=d,
+                       drop=drops[2])
+        return ('last', x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, xl, ql, user, drops)
 
     # ---------------------------------------------------------------- backward
     def backward(self, d_user):
@@ -335,7 +354,7 @@ class SASRecTower:
         ops.seq_prep_ln_bwd(table, pos, fp.p('LayerNorm.weight'), index, self.mean0, self.rstd0, dx, drows,
                             fp.g('LayerNorm.weight'), fp.g('LayerNorm.bias'),
                             fp.g('position_embedding.weight') if self.causal else None, tok_inv=pk['tok_inv'],
-                            shards=eng.seq_shards)
+                            shards=eng.seq_shards, drop=self.drop0)
         eng.add_seq_rowgrad(item_seq, drows)
 
     def _layer_bwd_full(self, i, st, dx, item_seq, pk):
@@ -343,27 +362,31 @@ class SASRecTower:
         B, L = item_seq.shape
         d, I, H, T, prec, n = self.d, self.I, self.H, B * L, eng.prec, pk['n']
         a, f = self._names(i)
-        _, x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, _x2 = st
-        # x2 = LN(z2), z2 = ffn(x1) + x1.  Bias gradients ride on the kernels that produce the corresponding dy.  Every
+        _, x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, _x2, drops = st
+        # x2 = LN(z2), z2 = dropout(ffn(x1)) + x1.  Bias gradients ride on the kernels that produce the corresponding dy.  Every
         # token-reduction GEMM (dW = dy^T x) has one operand written by an LN kernel, whose rows [n_tok, roundup32) are zero.
+        # With dropout the LN backward emits two gradients: dz (residual branch) and dz * mask (linear branch, `dy`).
         dz2 = ws.get('dz2', (T, d))
+        dy2 = ws.get('dz2m', (T, d)) if drops[2] is not None else dz2
         ops.add_ln_bwd(z2, fp.p(f + 'LayerNorm.weight'), m2, r2, dx, dz2, fp.g(f + 'LayerNorm.weight'),
-                       fp.g(f + 'LayerNorm.bias'), dzsum=fp.g(f + 'dense_2.bias'), rows_dev=n)
+                       fp.g(f + 'LayerNorm.bias'), dzsum=fp.g(f + 'dense_2.bias'), rows_dev=n, drop=drops[2], dZdrop=dy2)
         dh = ws.get('dh', (T, I))
-        # dh = (dz2 @ W2) * act'(hpre), db1 += colsum(dh): one GEMM with a fused epilogue
-        _lin_bwd(dz2, T, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'), None, prec=prec,
+        # dh = (dy2 @ W2) * act'(hpre), db1 += colsum(dh): one GEMM with a fused epilogue
+        _lin_bwd(dy2, T, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'), None, prec=prec,
                  dact=hpre, act=self.act, dx_colsum=fp.g(f + 'dense_1.bias'), rows_dev=n)
         # dx1 = dz2 (residual) + dh @ W1   -> accumulate into dz2
         _lin_bwd(dh, T, I, x1, d, fp.p(f + 'dense_1.weight'), dz2, fp.g(f + 'dense_1.weight'), None,
                  accumulate_dx=True, prec=prec, rows_dev=n)
         # x1 = LN(z1), z1 = attn_out + x
         dz1 = ws.get('dz1_%d' % (i % 2), (T, d))     # becomes this layer's input gradient (no copy)
+        dy1 = ws.get('dz1m', (T, d)) if drops[1] is not None else dz1
         ops.add_ln_bwd(z1, fp.p(a + 'LayerNorm.weight'), m1, r1, dz2, dz1, fp.g(a + 'LayerNorm.weight'),
-                       fp.g(a + 'LayerNorm.bias'), dzsum=fp.g(a + 'dense.bias'), rows_dev=n)
+                       fp.g(a + 'LayerNorm.bias'), dzsum=fp.g(a + 'dense.bias'), rows_dev=n, drop=drops[1], dZdrop=dy1)
         dctx = ws.get('dctx', (T, d))
-        _lin_bwd(dz1, T, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec, rows_dev=n)
+        _lin_bwd(dy1, T, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec, rows_dev=n)
         dqkv = ws.get('dqkv', (T, 3 * d))
-        ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv, offs=pk['offs'], tok_src=pk['tok_src'])
+        ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv, offs=pk['offs'], tok_src=pk['tok_src'],
+                     drop=drops[0])
         wqkv, gwqkv = fp.span(a + 'query.weight', a + 'value.weight')
         _, gbqkv = fp.span(a + 'query.bias', a + 'value.bias')
         # dx = dz1 (residual) + dqkv @ Wqkv  -> accumulate into dz1
@@ -377,23 +400,25 @@ class SASRecTower:
         B, L = item_seq.shape
         d, I, H, T, prec, n = self.d, self.I, self.H, B * L, eng.prec, pk['n']
         a, f = self._names(i)
-        _, x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, xl, ql, _user = st
+        _, x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, xl, ql, _user, drops = st
         dz2 = ws.get('dz2l', (B, d))
+        dy2 = ws.get('dz2ml', (B, d)) if drops[2] is not None else dz2
         ops.add_ln_bwd(z2, fp.p(f + 'LayerNorm.weight'), m2, r2, d_user, dz2, fp.g(f + 'LayerNorm.weight'),
-                       fp.g(f + 'LayerNorm.bias'), rows=B, d=d, dzsum=fp.g(f + 'dense_2.bias'))
+                       fp.g(f + 'LayerNorm.bias'), rows=B, d=d, dzsum=fp.g(f + 'dense_2.bias'), drop=drops[2], dZdrop=dy2)
         dh = ws.get('dhl', (B, I))
-        _lin_bwd(dz2, B, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'), None, prec=prec,
+        _lin_bwd(dy2, B, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'), None, prec=prec,
                  dact=hpre, act=self.act, dx_colsum=fp.g(f + 'dense_1.bias'))
         _lin_bwd(dh, B, I, x1, d, fp.p(f + 'dense_1.weight'), dz2, fp.g(f + 'dense_1.weight'), None,
                  accumulate_dx=True, prec=prec)
         dz1 = ws.get('dz1l', (B, d))
+        dy1 = ws.get('dz1ml', (B, d)) if drops[1] is not None else dz1
         ops.add_ln_bwd(z1, fp.p(a + 'LayerNorm.weight'), m1, r1, dz2, dz1, fp.g(a + 'LayerNorm.weight'),
-                       fp.g(a + 'LayerNorm.bias'), rows=B, d=d, dzsum=fp.g(a + 'dense.bias'))
+                       fp.g(a + 'LayerNorm.bias'), rows=B, d=d, dzsum=fp.g(a + 'dense.bias'), drop=drops[1], dZdrop=dy1)
         dctx = ws.get('dctxl', (B, d))
-        _lin_bwd(dz1, B, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec)
+        _lin_bwd(dy1, B, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec)
         dqkv, dql = ws.get('dqkv', (T, 3 * d)), ws.get('dql', (B, d))
         ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv, q_only_last=True, offs=pk['offs'],
-                     tok_src=pk['tok_src'], q_last=ql, dq_last=dql)
+                     tok_src=pk['tok_src'], q_last=ql, dq_last=dql, drop=drops[0])
         dkv = dqkv[:, d:]                                                  # [T, 2d], row stride 3d
         wqkv, gwqkv = fp.span(a + 'query.weight', a + 'value.weight')
         _, gbqkv = fp.span(a + 'query.bias', a + 'value.bias')
@@ -419,8 +444,9 @@ class GRUTower:
         self.eng = eng
         self.d = int(cfg['embedding_size'])
         self.Hd = int(cfg.get('hidden_size', self.d))
-        if float(cfg.get('dropout_prob', 0) or 0) > 0:
-            raise ValueError('unirec_b200: dropout_prob > 0 is not implemented in the fused GRU tower yet')
+        self.p_emb = float(cfg.get('dropout_prob', 0) or 0)        # nn.Dropout on the gathered rows, gru.py:29
+        if not 0.0 <= self.p_emb < 1.0:
+            raise ValueError('dropout_prob must lie in [0, 1), got %r' % (self.p_emb,))
 
     @staticmethod
     def flat_order(model):
@@ -434,6 +460,8 @@ class GRUTower:
         table, index = eng.seq_rows_source(item_seq)
         x = ws.get('gru_x', (B * L, d))
         ops.gather_rows(table, index, out=x)
+        self.drop0 = ops.Drop(eng.rng, self.p_emb, 0) if (self.p_emb > 0 and eng.model.training) else None
+        ops.dropout_rows(x, self.drop0)
         gi = ws.get('gru_gi', (B * L, 3 * Hd))
         _lin_fwd(x, B * L, d, fp.p('gru_layers.weight_ih_l0'), fp.p('gru_layers.bias_ih_l0'), 3 * Hd, gi, prec=prec)
         hs = ws.get('gru_h', (L + 1, B, Hd))
@@ -472,6 +500,7 @@ class GRUTower:
         drows = ws.get('drows', (B * L, d))
         _lin_bwd(dgi, B * L, 3 * Hd, self.x, d, fp.p('gru_layers.weight_ih_l0'), drows, fp.g('gru_layers.weight_ih_l0'),
                  fp.g('gru_layers.bias_ih_l0'), prec=prec)
+        ops.dropout_rows(drows, self.drop0)
         eng.add_seq_rowgrad(item_seq, drows)
 
 
@@ -594,6 +623,18 @@ class Engine:
         self.ws = Workspace(dev)
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._rowgrads = {}
+        # dropout counter state (csrc/dropout.cuh): (seed, training step).  The step advances on the device at the start of every
+        # training forward_loss, so a replayed CUDA graph draws fresh masks; ranks draw from different seeds.
+        seed = int(cfg.get('seed', 2022) or 0) + 0x9E3779B97F4A7C15 * int(getattr(m, 'shard_rank', 0) or 0)
+        self.rng = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+        self.uses_dropout = any(float(cfg.get(k, 0) or 0) > 0 for k in
+                                (('hidden_dropout_prob', 'attn_dropout_prob') if self.tower_kind == 'sasrec' else
+                                 ('dropout_prob',) if self.tower_kind == 'gru' else ()))
+
+    def set_dropout_state(self, seed, next_step):
+        """The next training forward draws the masks of (seed, next_step) -- tests replay a known mask set."""
+        self.ensure_ready()
+        self.rng.copy_(torch.tensor([int(seed), int(next_step) - 1], dtype=torch.int64))
 
     # ---- overlap of the row-sparse table update with the encoder (single-table sequence towers) ----
     def _overlap_rowgrad(self):
@@ -669,6 +710,8 @@ class Engine:
         B, N = item_id.shape
         for rg in self._rowgrads.values():
             rg.reset()
+        if self.uses_dropout and m.training:
+            ops.rng_advance(self.rng)
         early_rg = self._overlap_rowgrad()
         if early_rg is not None:
             self._early_link(early_rg, item_id, item_seq)

@@ -106,21 +106,66 @@ def _i32(t):
     return _ptr(t, torch.int32) if t is not None else None
 
 
-def seq_prep_ln_fwd(table, pos, gamma, beta, eps, item_seq, Y, mean, rstd, tok_src=None, n_tok=None, shards=None):
+class Drop:
+    """One dropout site of one step: (rng device int64[2] = (seed, step), p, site id) plus the map from buffer rows to original
+    token positions (row_pos tensor, or r * pos_mul + pos_add).  csrc/dropout.cuh."""
+    __slots__ = ('rng', 'p', 'site', 'row_pos', 'pos_mul', 'pos_add')
+
+    def __init__(self, rng, p, site, row_pos=None, pos_mul=1, pos_add=0):
+        self.rng, self.p, self.site, self.row_pos, self.pos_mul, self.pos_add = rng, float(p), int(site), row_pos, int(pos_mul), int(pos_add)
+
+
+def _drop3(drop):
+    """(rng pointer, p, site) of a Drop, or the identity triple."""
+    if drop is None or drop.p <= 0.0:
+        return None, 0.0, 0
+    return _ptr(drop.rng, torch.int64), drop.p, drop.site
+
+
+def _drop6(drop):
+    if drop is None or drop.p <= 0.0:
+        return None, 0.0, 0, None, 1, 0
+    return _ptr(drop.rng, torch.int64), drop.p, drop.site, _i32(drop.row_pos), drop.pos_mul, drop.pos_add
+
+
+def seq_prep_ln_fwd(table, pos, gamma, beta, eps, item_seq, Y, mean, rstd, tok_src=None, n_tok=None, shards=None, drop=None):
     """shards = (int64 device tensor of W peer pointers, W): `item_seq` holds global ids of a row-sharded table."""
     B, L = item_seq.shape
     _call('ur_seq_prep_ln_fwd_f32', _f32(table), _f32(pos), _f32(gamma), _f32(beta), float(eps),
           _ptr(item_seq, torch.int32), B, L, table.shape[1], _f32(Y), _f32(mean), _f32(rstd), _i32(tok_src), _i32(n_tok),
-          _ptr(shards[0], torch.int64) if shards else None, int(shards[1]) if shards else 0, _stream())
+          _ptr(shards[0], torch.int64) if shards else None, int(shards[1]) if shards else 0, *_drop3(drop), _stream())
     return Y
 
 
-def seq_prep_ln_bwd(table, pos, gamma, item_seq, mean, rstd, dY, dX, dgamma, dbeta, dpos, tok_inv=None, shards=None):
+def seq_prep_ln_bwd(table, pos, gamma, item_seq, mean, rstd, dY, dX, dgamma, dbeta, dpos, tok_inv=None, shards=None, drop=None):
     B, L = item_seq.shape
     _call('ur_seq_prep_ln_bwd_f32', _f32(table), _f32(pos), _f32(gamma), _ptr(item_seq, torch.int32), B, L,
           table.shape[1], _f32(mean), _f32(rstd), _f32(dY), _f32(dX), _f32(dgamma), _f32(dbeta), _f32(dpos), _i32(tok_inv),
-          _ptr(shards[0], torch.int64) if shards else None, int(shards[1]) if shards else 0, _stream())
+          _ptr(shards[0], torch.int64) if shards else None, int(shards[1]) if shards else 0, *_drop3(drop), _stream())
     return dX
+
+
+def dropout_rows(X, drop, rows=None, d=None, ld=None, rows_dev=None):
+    """X[r, :] *= mask in place (no-op when the site is off)."""
+    if drop is None or drop.p <= 0.0:
+        return X
+    d = d or X.shape[-1]
+    rows = rows if rows is not None else X.numel() // d
+    _call('ur_dropout_rows_f32', _f32(X), ld or d, rows, d, _i32(drop.row_pos), drop.pos_mul, drop.pos_add, _i32(rows_dev),
+          _ptr(drop.rng, torch.int64), drop.p, drop.site, _stream())
+    return X
+
+
+def dropout_mask(rng, p, site, rows, d, row_pos=None, pos_mul=1, pos_add=0, flat=False):
+    """The multipliers (0 or 1/(1-p)) of a dropout site as a [rows, d] tensor (test hook for the CPU oracle)."""
+    out = torch.empty(rows, d, dtype=torch.float32, device=rng.device)
+    _call('ur_dropout_mask_f32', _f32(out), rows, d, _i32(row_pos), int(pos_mul), int(pos_add), _ptr(rng, torch.int64), float(p),
+          int(site), int(flat), _stream())
+    return out
+
+
+def rng_advance(rng):
+    _call('ur_rng_advance', _ptr(rng, torch.int64), _stream())
 
 
 def ipc_export(t):
@@ -154,20 +199,26 @@ def zero_tail_rows(X, n_dev, width=None, ld=None):
     _call('ur_zero_tail_rows_f32', _f32(X), ld or X.shape[-1], width or X.shape[-1], _i32(n_dev), X.shape[0], _stream())
 
 
-def add_ln_fwd(X, R, gamma, beta, eps, Y, mean, rstd, rows=None, d=None, ldx=None, ldr=None, ldy=None, rows_dev=None):
+def add_ln_fwd(X, R, gamma, beta, eps, Y, mean, rstd, rows=None, d=None, ldx=None, ldr=None, ldy=None, rows_dev=None, drop=None):
+    """X <- dropout(X) + R; Y = LN(X)."""
     d = d or X.shape[-1]
     rows = rows if rows is not None else X.numel() // d
     _call('ur_add_ln_fwd_f32', _f32(X), ldx or d, _f32(R), ldr or d, _f32(gamma), _f32(beta), float(eps), rows, d,
-          _f32(Y), ldy or d, _f32(mean), _f32(rstd), _i32(rows_dev), _stream())
+          _f32(Y), ldy or d, _f32(mean), _f32(rstd), _i32(rows_dev), *_drop6(drop), _stream())
     return Y
 
 
 def add_ln_bwd(Z, gamma, mean, rstd, dY, dZ, dgamma, dbeta, dExtra=None, rows=None, d=None, ldz=None, lddy=None,
-               ldde=None, lddz=None, dzsum=None, rows_dev=None):
+               ldde=None, lddz=None, dzsum=None, rows_dev=None, drop=None, dZdrop=None):
+    """dZ = LN'(Z)(dY + dExtra).  With an active dropout site, dZdrop receives dZ * mask (gradient of the linear branch)."""
     d = d or Z.shape[-1]
     rows = rows if rows is not None else Z.numel() // d
+    on = drop is not None and drop.p > 0.0
+    if on and dZdrop is None:
+        raise ValueError('add_ln_bwd: an active dropout site needs the dZdrop output')
     _call('ur_add_ln_bwd_f32', _f32(Z), ldz or d, _f32(gamma), _f32(mean), _f32(rstd), _f32(dY), lddy or d,
-          _f32(dExtra), ldde or d, rows, d, _f32(dZ), lddz or d, _f32(dgamma), _f32(dbeta), _f32(dzsum), _i32(rows_dev), _stream())
+          _f32(dExtra), ldde or d, rows, d, _f32(dZ), lddz or d, _f32(dgamma), _f32(dbeta), _f32(dzsum), _i32(rows_dev),
+          _f32(dZdrop) if on else None, d, *_drop6(drop), _stream())
     return dZ
 
 
@@ -223,18 +274,19 @@ def colsum_accum(X, M, N, out, ldx=None, rows_dev=None):
 
 
 # ------------------------------------------------------------------ attention
-def attn_fwd(qkv, item_seq, H, dh, causal, ctx, lse, q_only_last=False, offs=None, tok_src=None, q_last=None):
+def attn_fwd(qkv, item_seq, H, dh, causal, ctx, lse, q_only_last=False, offs=None, tok_src=None, q_last=None, drop=None):
     B, L = item_seq.shape
     _call('ur_attn_fwd_f32', _f32(qkv), _ptr(item_seq, torch.int32), B, L, H, dh, int(causal), int(q_only_last),
-          _f32(ctx), _f32(lse), _i32(offs), _i32(tok_src), _f32(q_last), _stream())
+          _f32(ctx), _f32(lse), _i32(offs), _i32(tok_src), _f32(q_last), *_drop3(drop), _stream())
     return ctx
 
 
 def attn_bwd(qkv, item_seq, H, dh, causal, ctx, lse, dctx, dqkv, q_only_last=False, offs=None, tok_src=None, q_last=None,
-             dq_last=None):
+             dq_last=None, drop=None):
     B, L = item_seq.shape
     _call('ur_attn_bwd_f32', _f32(qkv), _ptr(item_seq, torch.int32), B, L, H, dh, int(causal), int(q_only_last),
-          _f32(ctx), _f32(lse), _f32(dctx), _f32(dqkv), _i32(offs), _i32(tok_src), _f32(q_last), _f32(dq_last), _stream())
+          _f32(ctx), _f32(lse), _f32(dctx), _f32(dqkv), _i32(offs), _i32(tok_src), _f32(q_last), _f32(dq_last), *_drop3(drop),
+          _stream())
     return dqkv
 
 

@@ -225,6 +225,8 @@ class ShardedEngine(Engine):
         B, N = item_id.shape
         for rg in self._rowgrads.values():
             rg.reset()
+        if self.uses_dropout and m.training:
+            ops.rng_advance(self.rng)
         if label is None:
             label = ws.get('default_label', (B, N), dtype=torch.int32, zero=True)
             label[:, 0] = 1
