@@ -259,7 +259,7 @@ class SASRecTower:
                 st = self._layer_fwd_full(i, x, item_seq, pk, tag)
             if save:
                 self.saved.append(st)
-            x = st[-1]
+            x = st[-2]                  # layer output (the tuple ends with the layer's dropout sites)
         if not self.trim_last:
             ops.gather_rows(x, pk['last'], out=user)
         return user
