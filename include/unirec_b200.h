@@ -208,6 +208,27 @@ int ur_build_batch(const int64_t* user_id, const int64_t* pos_item, int64_t B, c
                    int K, int L, int mask_mode, int seq_last, int64_t seed, int64_t step, int64_t* item_id, int32_t* label,
                    int32_t* item_seq, int64_t* item_seq_len, void* stream);
 
+/* ---- f3: one-vs-all ranking on the device (csrc/evalrank.cu): rank of the target among all items without a [B,V] score matrix;
+ * with row-sharded tables each rank counts over its own rows (world / rank as below) and the caller sums tscore and counts across ranks.
+ * replaces: Evaluator.evaluate_with_full_items unirec/facility/evaluation/evaluator_abc.py:190-278 (scores :232-241, history / target /
+ *           padding masking with NINF = -9999 :249-257) + get_rank unirec/facility/evaluation/onepos.py:20-31.
+ * score(s, g) = (<u_s, e_g> + item_bias[g] + user_bias[user_id[s]]) / tau, every dot accumulated in k order in one thread (bit-identical
+ * between the three kernels).  Exact ties are not counted (the reference breaks them with +-1e-8 noise, onepos.py:116-120).
+ *   ur_rank_target  tscore[s] = score(s, target[s]) if owned else 0
+ *   ur_rank_count   counts[s] += #{owned g : g != 0, g != target[s], score(s, g) > tscore[s]}
+ *   ur_rank_exclude counts[s] += sum over DISTINCT owned history items h (h != 0, h != target[s]) of [NINF > t] - [score(s,h) > t], plus
+ *                   [NINF > t] for the target's own slot; history = CSR (hist_ptr by user id, slices sorted ascending) */
+int ur_rank_target_f32(const float* table_local, int d, const float* user_emb, const int64_t* target, int64_t S,
+                       const float* item_bias /*nullable*/, const float* user_bias /*nullable*/, const int64_t* user_id /*nullable*/,
+                       float tau, int world, int rank, float* tscore, void* stream);
+int ur_rank_count_f32(const float* table_local, int64_t n_local, int d, const float* user_emb, int64_t S, const int64_t* target,
+                      const float* tscore, const float* item_bias /*nullable*/, const float* user_bias /*nullable*/,
+                      const int64_t* user_id /*nullable*/, float tau, int world, int rank, int32_t* counts, void* stream);
+int ur_rank_exclude_f32(const float* table_local, int d, const float* user_emb, int64_t S, const int64_t* target, const float* tscore,
+                        const float* item_bias /*nullable*/, const float* user_bias /*nullable*/, const int64_t* user_id /*nullable*/,
+                        float tau, int world, int rank, const int64_t* hist_ptr /*nullable*/, const int32_t* hist_sorted /*nullable*/,
+                        int64_t n_hist_users, int32_t* counts, void* stream);
+
 /* ---- Row-sharded tables (multi-GPU): rank r of `world` owns rows {id : id % world == r} at local index id / world.
  * These replace the reference's replicated tables + DDP all-reduce of dense [V,d] gradients
  * (unirec/model/base/reco_abc.py:167-170, unirec/facility/trainer.py:67,346) together with NCCL collectives issued by the host

@@ -42,6 +42,26 @@ def main(name='sasrec_softmax', p2p='1'):
     sd = {k: v for k, v in g.params.items()}
     sd['item_embedding.weight'] = sharding.shard_table(g.params['item_embedding.weight'], W, r)
     model.load_state_dict(sd)
+    # ---- evaluation with sharded tables: every rank runs the SAME full batch, owners contribute, ranks sum ----
+    from unirec_b200 import ops
+    model.eval()
+    full = {k: v.to(dev) for k, v in g.fwd_batch().items()}
+    _, s_eval, u_eval, it_eval = model(**full)
+    _, so, uo, _ = O.forward(g.model, g.params, g.cfg, **g.fwd_batch())
+    assert rel_err(u_eval.cpu(), uo) < 1e-3 and rel_err(s_eval.cpu(), so) < 1e-3, (rel_err(u_eval.cpu(), uo), rel_err(s_eval.cpu(), so))
+    assert torch.equal(it_eval.cpu(), g.params['item_embedding.weight'][g.batch['item_id']])          # bit-exact row gather
+    target = full['item_id'].view(full['item_id'].shape[0], -1)[:, 0].contiguous()
+    counts = model._engine.rank_one_vs_all(u_eval, target, user_id=full.get('user_id'))
+    ft = g.params['item_embedding.weight'].to(dev)
+    t1 = torch.empty(target.numel(), device=dev)
+    c1 = torch.zeros(target.numel(), dtype=torch.int32, device=dev)
+    ops.rank_target(ft, u_eval, target, t1, tau=model.tau)
+    ops.rank_count(ft, u_eval, target, t1, c1, tau=model.tau)
+    ops.rank_exclude(ft, u_eval, target, t1, c1, tau=model.tau)
+    assert torch.equal(counts, c1), (counts, c1)
+    if W > 1:
+        full_np = model.forward_all_item_emb()
+        assert (torch.from_numpy(full_np) == g.params['item_embedding.weight']).all()
     model.train()
     model._ur_fast_grads = True
     lr = float(cfg['learning_rate'])

@@ -356,3 +356,31 @@ def test_trainer_cuda_graph_step_matches_eager(name, tmp_path):
         if k.endswith('key.bias'):
             continue
         assert rel_err(s1[k], s0[k]) < 1e-4, (k, rel_err(s1[k], s0[k]))
+
+
+def test_frozen_parameters_do_not_move():
+    """Trainer.load_model(freeze) sets requires_grad = False (reference trainer.py:383-386): the fused optimizer must leave those
+    parameters alone -- dense ones (runs of the flat buffer) and whole tables."""
+    from unirec_b200.facility.optim import FusedOptimizer
+    g = Golden('sasrec_softmax')
+    model, cfg = cuda_model(g)
+    model.train()
+    model._ur_fast_grads = True
+    frozen = ['item_embedding.weight', 'trm_encoder.layer.0.feed_forward.dense_1.weight', 'LayerNorm.bias']
+    for n, p in model.named_parameters():
+        if n in frozen:
+            p.requires_grad = False
+    opt = FusedOptimizer(model, 'adam', lr=0.05, weight_decay=0.01)
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for _ in range(2):
+        loss = model(**to_dev(g.fwd_batch()))[0]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    after = model.state_dict()
+    for k in before:
+        if k in frozen:
+            assert torch.equal(after[k], before[k]), k
+    assert not torch.equal(after['trm_encoder.layer.0.feed_forward.dense_2.weight'], before['trm_encoder.layer.0.feed_forward.dense_2.weight'])
+    assert not torch.equal(after['position_embedding.weight'], before['position_embedding.weight'])
+    assert int((model._engine.rowgrad(model.item_embedding.weight).head != -1).sum()) == 0

@@ -89,3 +89,28 @@ def test_sharded_checkpoint_gather_and_localize_gloo_world2():
     out = mgr.dict()
     mp.spawn(_ckpt_worker, args=(2, 29713, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}, dict(out)
+
+
+def test_device_loader_gives_every_rank_the_same_number_of_equal_batches():
+    """ADVICE r1: order[rank::world] left ranks with sample counts differing by one -> different step counts / last-batch sizes under
+    fixed-shape collectives.  The stream is padded by wrap-around (accelerate's even_batches)."""
+    import numpy as np
+    from unirec_b200.data.device_loader import DeviceBatchLoader
+
+    class DS:
+        return_key_2_index = {'user_id': 0, 'item_id': 1, 'label': 2}
+
+        def __init__(self, n):
+            self.user_id = np.arange(1, n + 1, dtype=np.int64)
+            self.item_id = np.arange(1, n + 1, dtype=np.int64)
+
+        def __len__(self):
+            return len(self.user_id)
+
+    for n, world, bs in [(1001, 8, 16), (64, 8, 8), (17, 4, 5), (5, 8, 2)]:
+        for drop_last in (False, True):
+            loaders = [DeviceBatchLoader(DS(n), bs, 'cpu', 4, n + 1, n + 1, rank=r, world=world, drop_last=drop_last)
+                       for r in range(world)]
+            assert len({len(ld) for ld in loaders}) == 1
+            assert len({ld._my_count() for ld in loaders}) == 1
+            assert loaders[0]._my_count() * world >= n

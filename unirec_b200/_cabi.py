@@ -51,6 +51,9 @@ SIGNATURES = {
     'ur_clip_coef_f32': 'pfpp',
     'ur_step_advance': 'ppp',
     'ur_build_batch': 'pplppp' + 'llpp' + 'iiii' + 'll' + 'pppp' + 'p',
+    'ur_rank_target_f32': 'pipplpppfiipp',
+    'ur_rank_count_f32': 'pliplpppppfiipp',
+    'ur_rank_exclude_f32': 'piplpppppfiipplpp',
     'ur_shard_gather_rows_f32': 'pipiliipp',
     'ur_shard_localize': 'piliilpp',
     'ur_score_partial_f32': 'pippli' + 'pppp' + 'ffii' + 'ppp',

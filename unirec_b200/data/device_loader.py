@@ -37,8 +37,11 @@ class DeviceBatchLoader:
         self.with_seq = 'item_seq' in dataset.return_key_2_index
 
     def _my_count(self):
+        """Samples per rank per epoch -- IDENTICAL on every rank: the stream is padded by wrapping around to a multiple of the world
+        size (accelerate's even_batches behaviour, unirec/facility/trainer.py:261), because the row-sharded step issues fixed-shape
+        collectives and every rank must run the same number of steps with the same batch sizes."""
         n = len(self.dataset)
-        return (n - self.rank + self.world - 1) // self.world
+        return (n + self.world - 1) // self.world
 
     def __len__(self):
         n = self._my_count()
@@ -51,6 +54,9 @@ class DeviceBatchLoader:
             order = torch.randperm(n, generator=g).to(self.device)
         else:
             order = torch.arange(n, device=self.device)
+        pad = self._my_count() * self.world - n
+        if pad:                                        # wrap around: every rank gets the same number of samples
+            order = torch.cat([order, order[:pad]])
         order = order[self.rank::self.world]          # per-rank sharding of the sample stream (accelerate's prepared loader)
         self.epoch += 1
         ptr, hitems, hsorted = self.hist if self.hist is not None else (None, None, None)

@@ -696,6 +696,44 @@ class Engine:
                        score_clip=m.SCORE_CLIP, norm_host=1.0, scores=scores, loss_vec=lv)
         return scores.view(item_id.shape)
 
+    # ---- evaluation helpers (overridden by the row-sharded engine) -------------------------------
+    def eval_shard(self):
+        """(world, rank) of the row partition the local target table holds."""
+        return 1, 0
+
+    def eval_sum(self, t):
+        """Sum a per-user partial result over the ranks holding the table (identity for an unsharded table)."""
+        return t
+
+    def target_rows(self, idx):
+        """Rows of the target table for global ids `idx` (forward_item_emb, recommender.py:66-74)."""
+        return ops.gather_rows(self.table_for_target().data, idx)
+
+    def rank_one_vs_all(self, user_emb, target, user_id=None, hist=None):
+        """Number of catalogue items scoring above each user's target, history / padding / target excluded (csrc/evalrank.cu;
+        reference: evaluator_abc.py:190-278 + onepos.py:20-31).  hist = (ptr int64, items, sorted int32) CSR device tensors."""
+        self.ensure_ready()
+        m, ws = self.model, self.ws
+        B = user_emb.shape[0]
+        W, r = self.eval_shard()
+        table = self.table_for_target().data
+        ib = m.item_bias.data if m.has_item_bias else None
+        ub = m.user_bias.data if m.has_user_bias else None
+        uid = user_id.contiguous() if user_id is not None else None
+        if ub is not None and uid is None:
+            raise ValueError('one_vs_all ranking with user_bias needs user_id')
+        user_emb, target = user_emb.contiguous(), target.contiguous()
+        tscore = ws.get('rank_tscore', (B,))
+        counts = ws.get('rank_counts', (B,), dtype=torch.int32, zero=True)
+        kw = dict(item_bias=ib, user_bias=ub, user_id=uid, tau=m.tau, world=W, rank=r)
+        ops.rank_target(table, user_emb, target, tscore, **kw)
+        self.eval_sum(tscore)
+        ops.rank_count(table, user_emb, target, tscore, counts, **kw)
+        ops.rank_exclude(table, user_emb, target, tscore, counts, hist_ptr=hist[0] if hist else None,
+                         hist_sorted=hist[2] if hist else None, **kw)
+        self.eval_sum(counts)
+        return counts.clone()
+
     def forward_loss(self, user_id=None, item_id=None, label=None, item_seq=None, item_seq_len=None, reduction=True,
                      want_scores=False):
         self.ensure_ready()

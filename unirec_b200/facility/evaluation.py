@@ -2,8 +2,9 @@
 unirec/facility/evaluation/evaluator_abc.py:124-278 and onepos.py:104-175 for the protocols the hot path uses).
 
 one_vs_k  : the batch carries [B,1+K] candidates, positive first; rank = #negatives scoring above the positive.
-one_vs_all: rank of the target among ALL items, computed in item tiles (no [B,V] matrix is kept), items in the
-            user's history and the padding id excluded (reference masks them with NINF, evaluator_abc.py:249-265).
+one_vs_all: rank of the target among ALL items, counted on the device by csrc/evalrank.cu (no [B,V] matrix; history, padding id
+            and the target's own slot masked with NINF like evaluator_abc.py:249-257; row-sharded tables: every rank counts over
+            the rows it owns and the counts are summed).
 Metrics follow the reference definitions for a single positive: hit@k = [rank<k], ndcg@k = [rank<k]/log2(rank+2),
 mrr@k = [rank<k]/(rank+1), group_auc = fraction of candidates ranked below the positive.
 """
@@ -27,15 +28,19 @@ class RankEvaluator(object):
         self.user_history = user_history
         self.item_tile = 1 << 16
 
-    def _history_tensor(self, user_ids, device):
-        uh = self.user_history
-        rows = [np.asarray(uh[int(u)]) if uh is not None and int(u) < len(uh) and uh[int(u)] is not None else np.zeros(0, np.int64)
-                for u in user_ids.tolist()]
-        width = max(1, max(len(r) for r in rows))
-        out = np.zeros((len(rows), width), dtype=np.int64)
-        for i, r in enumerate(rows):
-            out[i, :len(r)] = r
-        return torch.from_numpy(out).to(device)
+    def _history_csr(self, device):
+        """The users' histories as CSR device tensors (ptr, items, sorted), built once (unirec_b200/data/history.py)."""
+        if self.user_history is None:
+            return None
+        key = str(device)
+        cache = self.__dict__.setdefault('_hist_dev', {})
+        if key not in cache:
+            from unirec_b200.data.history import UserHistoryCSR
+            uh = self.user_history
+            if not isinstance(uh, UserHistoryCSR):
+                uh = UserHistoryCSR.from_object_array(uh)
+            cache[key] = uh.device_tensors(device)
+        return cache[key]
 
     @torch.no_grad()
     def _ranks(self, model, samples):
@@ -45,47 +50,15 @@ class RankEvaluator(object):
                 scores = scores.reshape(-1, self.group_size)
             pos = scores[:, :1]
             return (scores[:, 1:] > pos).sum(1), scores.shape[1]
-        # one_vs_all
+        # one_vs_all: rank of the target among all items, counted by ur_rank_count / ur_rank_exclude (csrc/evalrank.cu) over the rows
+        # this rank owns -- no [B, V] score matrix, no host round trip, history / padding / target excluded on the device
         keys = inspect.signature(model.forward_user_emb).parameters
         user = model.forward_user_emb(**{k: v for k, v in samples.items() if k in keys})
-        table = model.forward_all_item_emb(numpy=False)
-        bias = model.item_bias.data if model.has_item_bias else None
-        target = samples['item_id'].reshape(samples['item_id'].shape[0], -1)[:, 0].long()
-        t_emb = table[target]
-        pos = (user * t_emb).sum(-1, keepdim=True)
-        if bias is not None:
-            pos = pos + bias[target].unsqueeze(1)
-        V = table.shape[0]
-        greater = torch.zeros(user.shape[0], dtype=torch.int64, device=user.device)
-        for s in range(0, V, self.item_tile):
-            e = min(V, s + self.item_tile)
-            sc = user @ table[s:e].t()
-            if bias is not None:
-                sc = sc + bias[s:e]
-            greater += (sc > pos).sum(1)
-        hist = self._history_tensor(samples['user_id'], user.device) if 'user_id' in samples else None
-        excl = torch.zeros_like(greater)
-        pad_sc = (user * table[0]).sum(-1, keepdim=True) + (bias[0] if bias is not None else 0.0)
-        excl += (pad_sc > pos).squeeze(1).long()
-        if hist is not None:
-            hs = torch.einsum('bd,bhd->bh', user, table[hist])
-            if bias is not None:
-                hs = hs + bias[hist]
-            live = (hist != 0) & (hist != target.unsqueeze(1))
-            # a history item listed twice must be excluded once: keep the first occurrence only
-            srt, _ = torch.sort(hist, dim=1)
-            dup_total = ((srt[:, 1:] == srt[:, :-1]) & (srt[:, 1:] != 0)).sum(1)
-            cnt = ((hs > pos) & live).sum(1)
-            if int(dup_total.sum()) > 0:
-                first = torch.ones_like(hist, dtype=torch.bool)
-                for b in torch.nonzero(dup_total).flatten().tolist():
-                    seen = set()
-                    for j, it in enumerate(hist[b].tolist()):
-                        first[b, j] = it not in seen
-                        seen.add(it)
-                cnt = ((hs > pos) & live & first).sum(1)
-            excl += cnt
-        return greater - excl, V - 1
+        target = samples['item_id'].reshape(samples['item_id'].shape[0], -1)[:, 0].long().contiguous()
+        user_id = samples['user_id'].long().contiguous() if 'user_id' in samples else None
+        hist = self._history_csr(user.device) if user_id is not None else None
+        counts = model._engine.rank_one_vs_all(user, target, user_id=user_id, hist=hist)
+        return counts.long(), int(model.n_items)
 
     @torch.no_grad()
     def evaluate(self, data, model, verbose=0, predict_only=False):

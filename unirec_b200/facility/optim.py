@@ -88,6 +88,27 @@ class FusedOptimizer(torch.optim.Optimizer):
             done.record(eng._side)
         self._early = (rg, done)
 
+    def _trainable_ranges(self, eng):
+        """[(begin, end)] element ranges of the flat buffer covering the parameters with requires_grad (usually one range)."""
+        named = dict(self.model.named_parameters())
+        key = tuple(bool(named[n].requires_grad) for n in eng.flat.names)
+        cached = getattr(self, '_ranges', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        ranges = []
+        for n, on in zip(eng.flat.names, key):
+            off, cnt, _ = eng.flat.offsets[n]
+            end = off + (cnt + 3) // 4 * 4
+            if not on:
+                continue
+            if ranges and ranges[-1][1] == off:
+                ranges[-1][1] = end
+            else:
+                ranges.append([off, end])
+        ranges = [(a, min(b, eng.flat.size)) for a, b in ranges]
+        self._ranges = (key, ranges)
+        return ranges
+
     # ---- step -----------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None):
@@ -97,6 +118,9 @@ class FusedOptimizer(torch.optim.Optimizer):
         lr, wd, (b1, b2), eps = g['lr'], g['weight_decay'], g['betas'], g['eps']
         skip = eng.nan_flag
         dense_tables = self.model.table_update == 'dense'
+        for rg in eng.rowgrads():
+            if rg.specs and not rg.param.requires_grad and not rg.linked:      # frozen table: drop its gradient entries
+                rg.reset()
         rowgrads = [rg for rg in eng.rowgrads() if rg.specs]
         early_rg = None
         for rg in rowgrads:
@@ -134,9 +158,14 @@ class FusedOptimizer(torch.optim.Optimizer):
 
         hyper = dict(lr=lr, beta1=b1, beta2=b2, eps=eps, weight_decay=wd, step_dev=st['step'], grad_scale_dev=scale,
                      skip_flag=skip)
-        if eng.flat.size:
-            ops.dense_opt(eng.flat.data, eng.flat.grad, st.get('m'), st.get('v'), self.mode, **hyper)
+        # frozen parameters (Trainer.load_model with `freeze`, unirec/facility/trainer.py:383-386: requires_grad = False) are left
+        # alone: the flat buffer is updated in maximal runs of trainable parameters, frozen tables are skipped
+        for o0, o1 in self._trainable_ranges(eng):
+            ops.dense_opt(eng.flat.data[o0:o1], eng.flat.grad[o0:o1], st['m'][o0:o1] if 'm' in st else None,
+                          st['v'][o0:o1] if 'v' in st else None, self.mode, **hyper)
         for p in eng.table_params():
+            if not p.requires_grad and not eng.rowgrad(p).specs:
+                continue
             ts = self._table_state(st, p)
             if dense_tables:
                 # reference semantics: every row moves every step (zero gradient where untouched)

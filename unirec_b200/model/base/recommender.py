@@ -103,7 +103,7 @@ class BaseRecommender(AbstractRecommender):
         self._engine.ensure_ready()
         from unirec_b200 import ops
         idx = items if items.dtype in (torch.int32, torch.int64) else items.long()
-        return ops.gather_rows(self._engine.table_for_target().data, idx.contiguous())
+        return self._engine.target_rows(idx.contiguous())          # row-sharded tables: owners contribute, ranks sum
 
     def item_embedding_for_user(self, item_seq, item_seq_features=None, time_seq=None):
         self._engine.ensure_ready()
@@ -126,6 +126,10 @@ class BaseRecommender(AbstractRecommender):
                                                           item_seq_len=item_seq_len, reduction=reduction,
                                                           want_scores=not return_loss_only)
             params = [p for p in self.parameters() if p.requires_grad]
+            if not params:          # fully frozen model (load_model with `freeze`): keep the loss a differentiable node
+                if getattr(self, '_frozen_anchor', None) is None or self._frozen_anchor.device != loss_raw.device:
+                    self._frozen_anchor = torch.zeros((), device=loss_raw.device, requires_grad=True)
+                params = [self._frozen_anchor]
             loss = _LossNode.apply(loss_raw, self, *params)
             if return_loss_only:
                 return loss, None, None, None
@@ -146,6 +150,10 @@ class BaseRecommender(AbstractRecommender):
     def forward_all_item_emb(self, batch_size=None, numpy=True):
         """All item embeddings (reference recommender.py:108-128).  Without item features this is the table itself."""
         w = self._engine.table_for_target().data.detach()
+        if self.shard_world > 1:        # collective: every rank re-assembles the full table in host memory
+            from unirec_b200.sharding import gather_full_table_all
+            full = gather_full_table_all(w, int(self.n_items), self.shard_world, self.shard_rank)
+            return full.numpy().astype(np.float32) if numpy else full
         return w.cpu().numpy().astype(np.float32) if numpy else w.clone()
 
     def get_all_item_bias(self):

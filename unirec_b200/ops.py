@@ -424,3 +424,30 @@ def score_dscore(z, item_id, label, lse_ny, world, rank, tau, score_clip, norm_d
     S, N = item_id.shape
     _call('ur_score_dscore_f32', _f32(z), _ptr(item_id, torch.int64), _ptr(label, torch.int32) if label is not None else None,
           _f32(lse_ny), S, N, world, rank, float(tau), float(score_clip), _f32(norm_dev), _f32(dscore), _stream())
+
+
+# ------------------------------------------------------------------ one-vs-all ranking (evaluation, csrc/evalrank.cu)
+def _i64(t):
+    return _ptr(t, torch.int64) if t is not None else None
+
+
+def rank_target(table_local, user_emb, target, tscore, item_bias=None, user_bias=None, user_id=None, tau=1.0, world=1, rank=0):
+    _call('ur_rank_target_f32', _f32(table_local), table_local.shape[1], _f32(user_emb), _i64(target), target.numel(),
+          _f32(item_bias), _f32(user_bias), _i64(user_id), float(tau), int(world), int(rank), _f32(tscore), _stream())
+    return tscore
+
+
+def rank_count(table_local, user_emb, target, tscore, counts, item_bias=None, user_bias=None, user_id=None, tau=1.0, world=1,
+               rank=0):
+    _call('ur_rank_count_f32', _f32(table_local), table_local.shape[0], table_local.shape[1], _f32(user_emb), target.numel(),
+          _i64(target), _f32(tscore), _f32(item_bias), _f32(user_bias), _i64(user_id), float(tau), int(world), int(rank),
+          _i32(counts), _stream())
+    return counts
+
+
+def rank_exclude(table_local, user_emb, target, tscore, counts, item_bias=None, user_bias=None, user_id=None, tau=1.0, world=1,
+                 rank=0, hist_ptr=None, hist_sorted=None):
+    _call('ur_rank_exclude_f32', _f32(table_local), table_local.shape[1], _f32(user_emb), target.numel(), _i64(target),
+          _f32(tscore), _f32(item_bias), _f32(user_bias), _i64(user_id), float(tau), int(world), int(rank), _i64(hist_ptr),
+          _i32(hist_sorted), (hist_ptr.numel() - 1) if hist_ptr is not None else 0, _i32(counts), _stream())
+    return counts

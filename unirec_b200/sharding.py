@@ -56,6 +56,28 @@ def unshard_tables(shards):
 SHARDED_TABLES = ('item_embedding.weight',)       # parameters stored row-sharded when table_shard_world > 1
 
 
+def gather_full_table_all(local, n_rows, world, rank, group=None, chunk_rows=1 << 20):
+    """Every rank gets the full [n_rows, d] table in host memory (forward_all_item_emb of a sharded model,
+    recommender.py:108-128): chunked all-gathers of equally sized (zero-padded) shard slices."""
+    d = local.shape[1]
+    full = torch.empty(n_rows, d, dtype=local.dtype)
+    rows_max = local_rows_count(n_rows, world, 0)
+    for c0 in range(0, rows_max, chunk_rows):
+        c1 = min(rows_max, c0 + chunk_rows)
+        mine = torch.zeros(c1 - c0, d, dtype=local.dtype, device=local.device)
+        have = max(0, min(local.shape[0], c1) - c0)
+        if have:
+            mine[:have] = local[c0:c0 + have].detach()
+        bufs = torch.empty(world, c1 - c0, d, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(bufs, mine, group=group)
+        host = bufs.cpu()
+        for src in range(world):
+            n_src = max(0, min(local_rows_count(n_rows, world, src), c1) - c0)
+            if n_src:
+                full[src + c0 * world:src + (c0 + n_src - 1) * world + 1:world] = host[src, :n_src]
+    return full
+
+
 def gather_full_table(local, n_rows, world, rank, group=None, chunk_rows=1 << 20):
     """Re-assemble a row-sharded [n_rows, d] table on rank 0 (host memory) for a reference-compatible checkpoint
     (§8 f4; reference dict: unirec/facility/trainer.py:389-398).  Shards travel in chunks of `chunk_rows` rows, so the
@@ -212,6 +234,39 @@ class ShardedEngine(Engine):
             return
         d_all = self._all_gather('drows', drows)                           # [W, B*L, d]
         self.rowgrad(self.table_for_seq()).add(keys, d_all.view(-1, d_all.shape[-1]), 1, None, 1)
+
+    # ---- evaluation: every rank runs the SAME evaluation batches (the eval loaders are not sharded across ranks), each rank works on
+    # the rows it owns and the partial results add up -- no table rows move ------------------------------------------------------
+    def eval_shard(self):
+        return self.world, self.rank
+
+    def eval_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def target_rows(self, idx):
+        idx = idx.contiguous()
+        out = torch.empty(tuple(idx.shape) + (self.table_for_target().shape[1],), dtype=torch.float32, device=self.device)
+        ops.shard_gather_rows(self.table_for_target().data, idx, self.world, self.rank, out)     # zeros where not owned
+        return self.eval_sum(out)
+
+    def scores_only(self, user_emb, item_id, user_id=None):
+        """_predict_layer without loss (eval / predict, recommender.py:76-96): owners score their entries, the rest is zero, sum."""
+        m, ws = self.model, self.ws
+        item_id2 = item_id.view(item_id.shape[0], -1).contiguous()
+        B, N = item_id2.shape
+        d = user_emb.shape[1]
+        z = torch.zeros(B, N, dtype=torch.float32, device=self.device)
+        state = ws.get('score_state_eval', (B, 4 + 2 * d))
+        ops.score_partial(self.table_for_target().data, user_emb.contiguous(), item_id2, self.world, self.rank, z, state,
+                          item_bias=m.item_bias.data if m.has_item_bias else None,
+                          user_bias=m.user_bias.data if m.has_user_bias else None,
+                          user_id=user_id if m.has_user_bias else None, tau=m.tau, score_clip=m.SCORE_CLIP)
+        self.eval_sum(z)
+        if m.SCORE_CLIP > 0:
+            z.clamp_(-m.SCORE_CLIP, m.SCORE_CLIP)
+        return z.view(item_id.shape)
 
     # ---- forward / backward ---------------------------------------------------------------------
     def forward_loss(self, user_id=None, item_id=None, label=None, item_seq=None, item_seq_len=None, reduction=True,
