@@ -383,4 +383,5 @@ def test_frozen_parameters_do_not_move():
             assert torch.equal(after[k], before[k]), k
     assert not torch.equal(after['trm_encoder.layer.0.feed_forward.dense_2.weight'], before['trm_encoder.layer.0.feed_forward.dense_2.weight'])
     assert not torch.equal(after['position_embedding.weight'], before['position_embedding.weight'])
-    assert int((model._engine.rowgrad(model.item_embedding.weight).head != -1).sum()) == 0
+    head = model._engine.rowgrad(model.item_embedding.weight).head
+    assert head is None or int((head != -1).sum()) == 0
