@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- training samples/s of the SASRec hot path (BASELINE.json metric) on N B200s, next to the CPU baseline.
+"""bench.py -- training samples/s of the sequential-recommender hot path (BASELINE.json metric) on N B200s, next to the CPU baseline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-One "step" = one training iteration over one synthetic batch: gather -> SASRec encoder -> sampled-softmax loss ->
-backward -> row-sparse table update + dense encoder update (unirec/facility/trainer.py:340-349).
-Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: same step through the public Trainer API with
-pinned-host inputs copied in and the loss read back every step.  `roofline`: the fused gather/score/loss kernel
-(HBM-bound), timed with CUDA events inside the timed region.  `cpu_baseline`: the oracle port of the reference step on
-the host cores (bounded sample).  See DESIGN.md section "Measurement".
+One "step" = one training iteration over one synthetic batch: gather -> tower (SASRec / GRU / sum-pool / MF) -> sampled-softmax or
+BPR loss -> backward -> row-sparse table update + dense encoder update (unirec/facility/trainer.py:340-349).
+Prints ONE JSON line (rank 0):
+  value      device-resident inputs, the step the product runs in steady state (Trainer.train_step: one CUDA graph per step)
+  e2e        same step through the public Trainer API with pinned-host batches copied in and the loss read back every step
+  roofline   the dominant kernels of the step (array `kernels`: fused score/loss, row-sparse Adam, encoder GEMM family,
+             attention), each timed live with CUDA events around its C-ABI call in an eager pass of the same steps; the
+             top-level fields describe the north-star kernel (fused gather+score+loss, HBM-bound)
+  cpu_baseline / gpu_eager_baseline   the oracle port of the reference step on the host cores / on the same GPU via torch
+             eager (dense gradients + dense Adam: the thing the SURVEY names as "to beat on the same box")
+See DESIGN.md section "Measurement".  Workloads = BASELINE.json configs c1..c5 plus the metric's own configuration (default).
 """
 import argparse
 import json
@@ -21,40 +26,67 @@ import threading
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# B = batch per GPU (weak scaling) unless 'global_B' is set (fixed global batch, split across the ranks)
 WORKLOADS = {
     # the configuration the BASELINE.json metric / north-star target is quoted on (fits one GPU: 5.1 GB table)
     'sasrec_d128_seq50_items10M_k1024_b1024': dict(model='SASRec', n_items=10_000_000, n_users=1_000_000, embedding_size=128,
                                                    hidden_size=128, n_layers=2, n_heads=2, inner_size=512, max_seq_len=50,
                                                    loss_type='softmax', K=1024, B=1024),
-    # BASELINE.json configs[1]
-    'sasrec_d128_seq50_items1M_k256_b1024': dict(model='SASRec', n_items=1_000_000, n_users=1_000_000, embedding_size=128,
-                                                 hidden_size=128, n_layers=2, n_heads=2, inner_size=512, max_seq_len=50,
-                                                 loss_type='softmax', K=256, B=1024),
-    # BASELINE.json configs[2]
-    'gru_d256_seq100_items5M_bpr5_b2048': dict(model='GRU', n_items=5_000_000, n_users=1_000_000, embedding_size=256,
-                                               hidden_size=256, max_seq_len=100, loss_type='bpr', K=5, B=2048),
+    # BASELINE.json configs[0] (the reference's CPU-runnable plumbing case, here on the GPU path)
+    'c1_mf_bpr_u10k_i5k_d64_b256': dict(model='MF', n_items=5_000, n_users=10_000, embedding_size=64, loss_type='bpr', K=1, B=256),
+    # configs[1]
+    'c2_sasrec_d128_seq50_items1M_k256_b1024': dict(model='SASRec', n_items=1_000_000, n_users=1_000_000, embedding_size=128,
+                                                    hidden_size=128, n_layers=2, n_heads=2, inner_size=512, max_seq_len=50,
+                                                    loss_type='softmax', K=256, B=1024),
+    # configs[2]
+    'c3_gru_d256_seq100_items5M_bpr5_b2048': dict(model='GRU', n_items=5_000_000, n_users=1_000_000, embedding_size=256,
+                                                  hidden_size=256, max_seq_len=100, loss_type='bpr', K=5, B=2048),
+    # configs[3] (8 x B200, row-sharded item table; global batch 4096)
+    'c4_sasrec_d256_L4_seq200_items10M_k4096_b4096': dict(model='SASRec', n_items=10_000_000, n_users=1_000_000, embedding_size=256,
+                                                          hidden_size=256, n_layers=4, n_heads=4, inner_size=1024, max_seq_len=200,
+                                                          loss_type='softmax', K=4096, global_B=4096),
+    # configs[4] (8 x B200 gather/scatter stress; global batch 2048, BPR with 5 negatives)
+    'c5_svdpp_d128_seq500_items50M_bpr5_b2048': dict(model='SVDPlusPlus', n_items=50_000_000, n_users=1_000_000, embedding_size=128,
+                                                     max_seq_len=500, loss_type='bpr', K=5, global_B=2048),
+    'c5_avghist_d128_seq500_items50M_bpr5_b2048': dict(model='AvgHist', n_items=50_000_000, n_users=1_000_000, embedding_size=128,
+                                                       max_seq_len=500, loss_type='bpr', K=5, global_B=2048),
     # tiny: CI / CPU-baseline sanity
     'sasrec_tiny': dict(model='SASRec', n_items=20_000, n_users=1000, embedding_size=64, hidden_size=64, n_layers=1, n_heads=2,
                         inner_size=128, max_seq_len=20, loss_type='softmax', K=32, B=128),
 }
+ALIASES = {'sasrec_d128_seq50_items1M_k256_b1024': 'c2_sasrec_d128_seq50_items1M_k256_b1024',
+           'gru_d256_seq100_items5M_bpr5_b2048': 'c3_gru_d256_seq100_items5M_bpr5_b2048'}
 DEFAULT_WORKLOAD = 'sasrec_d128_seq50_items10M_k1024_b1024'
 COMMON = dict(dataset='example', exp_name='bench', train_file_format='user-item', hidden_dropout_prob=0.0,
               attn_dropout_prob=0.0, dropout_prob=0.0, scheduler='none', optimizer='adam', learning_rate=1e-3,
               hidden_act='swish', layer_norm_eps=1e-10, use_position_emb=1)
+META_KEYS = ('K', 'B', 'global_B')
 
 
-def synthetic_batch(w, seed):
+def batch_per_gpu(w, world):
+    if 'global_B' in w:
+        if w['global_B'] % world:
+            raise SystemExit('global batch %d does not split over %d GPUs' % (w['global_B'], world))
+        return w['global_B'] // world
+    return w['B']
+
+
+def synthetic_batch(w, seed, B=None):
     """uniform ids in [1, V-1], left-padded item_seq with length ~ U{1..L}, positive in column 0."""
     import torch
     g = torch.Generator().manual_seed(seed)
-    V, U, B, K, L = w['n_items'], w['n_users'], w['B'], w['K'], w['max_seq_len']
-    lens = torch.randint(1, L + 1, (B,), generator=g)
-    seq = torch.randint(1, V, (B, L), generator=g, dtype=torch.int64)
-    seq = torch.where(torch.arange(L)[None, :] >= (L - lens)[:, None], seq, torch.zeros_like(seq)).to(torch.int32)
+    V, U, K = w['n_items'], w['n_users'], w['K']
+    B = B or w.get('B') or w['global_B']
     label = torch.zeros(B, 1 + K, dtype=torch.int32)
     label[:, 0] = 1
-    return dict(user_id=torch.randint(1, U, (B,), generator=g), item_id=torch.randint(1, V, (B, 1 + K), generator=g),
-                label=label, item_seq=seq, item_seq_len=lens)
+    out = dict(user_id=torch.randint(1, U, (B,), generator=g), item_id=torch.randint(1, V, (B, 1 + K), generator=g), label=label)
+    if w['model'] != 'MF':
+        L = w['max_seq_len']
+        lens = torch.randint(1, L + 1, (B,), generator=g)
+        seq = torch.randint(1, V, (B, L), generator=g, dtype=torch.int64)
+        seq = torch.where(torch.arange(L)[None, :] >= (L - lens)[:, None], seq, torch.zeros_like(seq)).to(torch.int32)
+        out.update(item_seq=seq, item_seq_len=lens)
+    return out
 
 
 def measured_peaks():
@@ -64,6 +96,16 @@ def measured_peaks():
             p = json.load(f)
         return float(p['hbm_gbs']), float(p.get('bf16_tflops_sustained', p.get('bf16_tflops', 1590.0))), 'measured'
     return 6650.0, 1590.0, 'fallback'
+
+
+def ncu_traffic(workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/ncu_traffic.json, keyed by workload / GPU count / C-ABI entry point); None when no capture exists."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return json.load(f).get('%s@%d' % (workload, world), {})
 
 
 class ClockSampler:
@@ -98,28 +140,94 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
+def oracle_cfg(w):
+    cfg = dict(COMMON)
+    cfg.update({k: v for k, v in w.items() if k not in META_KEYS})
+    return cfg
+
+
+def cpu_sample_workload(w):
+    """Bounded CPU sample of a workload: the reference step materialises [B,1+K,d] activations plus dense [V,d] gradients and Adam
+    state for every table, so the big configurations are timed at reduced batch / catalogue (per-sample throughput is what is
+    compared; the reduction is stated in `sample`)."""
+    w = dict(w)
+    note = []
+    B = w.get('B') or w['global_B']
+    V, d, K = w['n_items'], w['embedding_size'], w['K']
+    tables = 2 if w['model'] in ('SVDPlusPlus',) or (w['model'] == 'AvgHist') else 1
+    if V * d * 4 * 4 * tables > 24e9:                       # params + grads + 2 Adam moments beyond ~24 GB of host RAM
+        w['n_items'] = int(24e9 / (d * 16 * tables))
+        note.append('V reduced %d -> %d (host RAM: dense grads + Adam state)' % (V, w['n_items']))
+    per_sample = (1 + K) * d * 4 * 3 + w.get('max_seq_len', 0) * d * 4 * (30 if w['model'] == 'SASRec' else 6)
+    Bc = B
+    while Bc > 16 and Bc * per_sample > 6e9:
+        Bc //= 2
+    if Bc != B:
+        note.append('B reduced %d -> %d' % (B, Bc))
+    w.pop('global_B', None)
+    w['B'] = Bc
+    return w, '; '.join(note) if note else 'full workload'
+
+
 def run_reference(args, w, name):
     """--impl reference: the reference step (oracle port, dense grads + dense Adam) on the host cores."""
-    import torch
     from oracle import cpu_baseline
-    cfg = dict(COMMON)
-    cfg.update({k: v for k, v in w.items() if k not in ('K', 'B')})
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    batches = [synthetic_batch(w, 100 + i) for i in range(2)]
-    if w['model'] == 'MF':
-        batches = [{k: b[k] for k in ('user_id', 'item_id', 'label')} for b in batches]
-    sps, ms, threads = cpu_baseline.time_steps(w['model'], cfg, batches, args.steps, args.warmup)
+    wc, note = cpu_sample_workload(w)
+    batches = [synthetic_batch(wc, 100 + i) for i in range(2)]
+    sps, ms, threads = cpu_baseline.time_steps(wc['model'], oracle_cfg(wc), batches, args.steps, args.warmup)
     line = {'metric': 'training samples/sec', 'value': sps, 'unit': 'samples/s', 'impl': 'reference', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': name, 'batch_per_step': w['B'], 'optimizer': 'dense Adam (reference semantics)'},
+            'config': {'workload': name, 'batch_per_step': wc['B'], 'optimizer': 'dense Adam (reference semantics)'},
             'cpu_baseline': {'value': sps, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d timed steps of the full workload (B=%d) after %d warm-up' % (args.steps, w['B'], args.warmup)},
+                             'sample': '%d timed steps (B=%d, V=%d) after %d warm-up; %s' % (args.steps, wc['B'], wc['n_items'], args.warmup, note)},
             'e2e': {'value': sps, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+def gpu_eager_baseline(w, dev, steps=3, warmup=2):
+    """The oracle port of the reference step run by torch eager on the same GPU (ATen / cuBLAS with TF32 off, dense [V,d] gradients,
+    dense Adam over every table row): the SURVEY's 'thing to beat on the same box'.  Measurement leg only."""
+    import torch
+    from oracle import cpu_baseline
+    from oracle import unirec_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = oracle_cfg(w)
+    p = {k: v.to(dev) for k, v in cpu_baseline.init_params(w['model'], cfg).items()}
+    leaves = {k: v.requires_grad_(True) for k, v in p.items()}
+    opt = torch.optim.Adam(list(leaves.values()), lr=1e-3)
+    B = w.get('B') or w['global_B']
+    batches = [{k: v.to(dev) for k, v in synthetic_batch(w, 500 + i, B).items()} for i in range(2)]
+
+    def one(i):
+        loss = O.forward(w['model'], leaves, cfg, **batches[i % 2])[0]
+        opt.zero_grad()
+        loss.backward()
+        with torch.no_grad():
+            for k in O.PADDING_TABLES:
+                if k in leaves and leaves[k].grad is not None:
+                    leaves[k].grad[0] = 0
+        opt.step()
+
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del leaves, p, opt, batches
+    torch.cuda.empty_cache()
+    return {'value': B / (ms / 1e3), 'unit': 'samples/s', 'ms_per_step': ms, 'kind': 'oracle port, torch eager CUDA, fp32 (TF32 off), '
+            'dense gradients + dense Adam', 'sample': '%d timed steps of the full workload after %d warm-up' % (steps, warmup)}
 
 
 def main():
@@ -127,20 +235,25 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=None)
-    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(ALIASES))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--gemm-precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-eager-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='keep Trainer.train_step eager (ncu launch lists)')
+    ap.add_argument('--no-loss-check', action='store_true', help='N>1: skip the single-GPU cross-check of the first loss')
+    ap.add_argument('--dropout', type=float, default=0.0, help='hidden/attn (SASRec) or embedding (GRU) dropout of the timed steps')
+    ap.add_argument('--batch-per-gpu', type=int, default=None)
     ap.add_argument('--shard-p2p', type=int, default=1, help='row-sharded tables: 1 = peer-memory reads over NVLink, 0 = NCCL exchange')
     ap.add_argument('--overlap', type=int, default=0, help='overlap_table_update mode (0 off, 1 early link, 2 + early update)')
     args = ap.parse_args()
     sys.argv = sys.argv[:1]
-    w = dict(WORKLOADS[args.workload])
+    name = ALIASES.get(args.workload, args.workload)
+    w = dict(WORKLOADS[name])
     if args.impl == 'reference':
         args.steps = args.steps if args.steps is not None else 2
         args.warmup = args.warmup if args.warmup is not None else 1
-        return run_reference(args, w, args.workload)
+        return run_reference(args, w, name)
     args.steps = args.steps if args.steps is not None else 50
     args.warmup = args.warmup if args.warmup is not None else 5
 
@@ -155,22 +268,24 @@ def main():
     world, rank, dev = acc.num_processes, acc.process_index, acc.device
     if world != args.gpus:
         raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N>1)' % (args.gpus, world))
-    B, K, L, d = w['B'], w['K'], w['max_seq_len'], w['embedding_size']
+    B = args.batch_per_gpu or batch_per_gpu(w, world)
+    K, d = w['K'], w['embedding_size']
+    L = w.get('max_seq_len', 0)
     cfg_args = dict(COMMON)
-    cfg_args.update({k: v for k, v in w.items() if k not in ('K', 'B')})
+    cfg_args.update({k: v for k, v in w.items() if k not in META_KEYS})
     cfg_args.update(batch_size=B, n_sample_neg_train=K, gemm_precision=args.gemm_precision, epochs=1,
                     output_path=os.path.join(ROOT, 'gpurun_out', 'bench_ckpt'), table_shard_world=world,
-                    overlap_table_update=args.overlap, cuda_graph=0 if args.no_graph else 1, shard_p2p=args.shard_p2p)
+                    overlap_table_update=args.overlap, cuda_graph=0 if args.no_graph else 1, shard_p2p=args.shard_p2p,
+                    table_init_device=1, hidden_dropout_prob=args.dropout, attn_dropout_prob=args.dropout, dropout_prob=args.dropout)
     cfg = argument_parser.parse_arguments(cfg_args, argv=[])
     cfg['device'] = dev
     general.init_seed(2022)
     model = general.get_class_instance(cfg['model'], 'unirec_b200/model')(cfg)
     trainer = Trainer(cfg, model, acc)
+    eng = model._engine
 
     n_pool = 8                      # distinct batches, rotated: no step re-reads the previous step's rows from L2
-    host = [synthetic_batch(w, 1000 * rank + i) for i in range(n_pool)]
-    if w['model'] == 'MF':
-        host = [{k: b[k] for k in ('user_id', 'item_id', 'label')} for b in host]
+    host = [synthetic_batch(w, 1000 * rank + i, B) for i in range(n_pool)]
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
@@ -180,46 +295,44 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm (`value`) ----
-    for i in range(args.warmup):
-        trainer.train_step(resident[i % n_pool])
-    barrier()
+    def timed(n, batches_of):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = None
+        for i in range(n):
+            last = trainer.train_step(batches_of(i))
+        b.record()
+        barrier()
+        return a.elapsed_time(b), last
+
+    # ---- `value`: device-resident inputs, the product's steady-state step (one CUDA graph per step when capturable) ----
+    for i in range(max(args.warmup, 3)):            # the first two eager iterations size the workspace, the third captures the graph
+        loss0 = trainer.train_step(resident[i % n_pool])
+        if i == 0:
+            first_loss = float(loss0)
+    graphed = bool(getattr(trainer, '_graphs', None)) and all('graph' in g for g in trainer._graphs.values())
     ops.LAUNCH_COUNT = 0
-    # sharded tables (N>1): the owner-side partial-softmax kernel is the row-gather kernel (same rows per rank per step)
-    ops.TIMED_OP, ops.TIMED_EVENTS = ('ur_score_loss_fwd_bwd_f32' if world == 1 else 'ur_score_partial_f32'), []
     clocks = ClockSampler(dev.index or 0)
     clocks.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = trainer.train_step(resident[(args.warmup + i) % n_pool])
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total, loss = timed(args.steps, lambda i: resident[(args.warmup + i) % n_pool])
     clk = clocks.stop()
-    launches = ops.LAUNCH_COUNT
-    kernel_ms = [a.elapsed_time(b) for a, b in ops.TIMED_EVENTS]
-    ops.TIMED_OP, ops.TIMED_EVENTS = None, []
     final_loss = float(loss)
 
-    # ---- same device-resident steps through the captured CUDA graph (Trainer.train_step's steady state) ----
-    ms_graph = float('nan')
-    if world == 1 and not args.no_graph:          # the row-sharded step (N > 1) is not graph-captured yet
-        for i in range(3):
-            trainer.train_step(resident[i % n_pool])
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for i in range(args.steps):
-            trainer.train_step(resident[(args.warmup + i) % n_pool])
-        g1.record()
-        barrier()
-        ms_graph = g0.elapsed_time(g1)
+    # ---- eager pass of the same steps: CUDA events around every C-ABI call -> per-kernel times (roofline block) ----
+    ops.PROFILE, ops.GEMM_LOG = {}, []
+    n_prof = min(args.steps, 10)
+    ms_eager, _ = timed(n_prof, lambda i: resident[(args.warmup + i) % n_pool])
+    torch.cuda.synchronize()
+    launches_per_step = sum(len(v) for v in ops.PROFILE.values()) / n_prof
+    breakdown = {k: sum(a.elapsed_time(b) for a, b in v) / n_prof for k, v in ops.PROFILE.items()}
+    gemm_log = ops.GEMM_LOG
+    ops.PROFILE, ops.GEMM_LOG = None, None
+    launches = int(round(launches_per_step * args.steps))
 
     # ---- end-to-end arm: pinned host inputs in, loss out, every step, through the public Trainer API ----
-    # Trainer.device_batches is the loader-side API of the trainer: it copies batch i+1 host->device on a copy stream while
-    # step i computes; every batch is copied from pinned host memory inside the timed region, every loss is read back.
+    # Trainer.device_batches copies batch i+1 host->device on a copy stream while step i computes; every batch is copied from
+    # pinned host memory inside the timed region, every loss is read back.
     def host_stream(n):
         for i in range(n):
             yield pinned[i % n_pool]
@@ -227,8 +340,7 @@ def main():
     for batch in trainer.device_batches(host_stream(3)):
         float(trainer.train_step(batch))
     barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for batch in trainer.device_batches(host_stream(args.steps)):
         float(trainer.train_step(batch))                   # device->host read of the step's loss
@@ -236,61 +348,140 @@ def main():
     barrier()
     ms_e2e = t0.elapsed_time(t1)
 
-    # ---- per-kernel breakdown (separate pass, events around every C-ABI call; not part of the timed numbers) ----
-    ops.PROFILE = {}
-    for i in range(3):
-        trainer.train_step(resident[i % n_pool])
-    torch.cuda.synchronize()
-    breakdown = {k: sum(a.elapsed_time(b) for a, b in v) / 3.0 for k, v in ops.PROFILE.items()}
-    ops.PROFILE = None
+    # live statistics of the last step (device scalars read once, after the timed regions)
+    n_uniq = {n: int(eng.rowgrad(p).n_uniq) for n, p in model.named_parameters() if eng._rowgrads.get(id(p)) is not None
+              and eng.rowgrad(p).n_uniq is not None}
+    live_frac = 1.0
+    if hasattr(eng.tower, 'pk') and L:
+        live_frac = float(eng.tower.pk['n']) / (B * L)
+    live_hist_rows = int((resident[0]['item_seq'] > 0).sum()) if L else 0
 
-    t = torch.tensor([ms_total, ms_e2e, ms_graph], dtype=torch.float64, device=dev)
+    # ---- correctness bit for multi-GPU runs (dropout off): the sharded job's loss on its first step equals one GPU running the
+    # same GLOBAL batch on the unsharded model (same seed -> the W shards are slices of the same initial table) ----
+    loss_check = None
+    if acc.distributed and args.dropout == 0.0 and w['n_items'] * d * 4 <= 6e9 and not args.no_loss_check:
+        gathered = {}
+        for k, v in resident[0].items():
+            buf = torch.empty((world,) + tuple(v.shape), dtype=v.dtype, device=dev)
+            dist.all_gather_into_tensor(buf, v.contiguous())
+            gathered[k] = buf.view((-1,) + tuple(v.shape[1:]))
+        if rank == 0:
+            cfg1 = argument_parser.parse_arguments(dict(cfg_args, table_shard_world=1, batch_size=B * world), argv=[])
+            cfg1['device'] = dev
+            general.init_seed(2022)
+            model1 = general.get_class_instance(cfg1['model'], 'unirec_b200/model')(cfg1).to(dev)
+            model1.train()
+            with torch.no_grad():
+                ref = float(model1(**gathered)[0])
+            rel = abs(first_loss - ref) / max(abs(ref), 1e-12)
+            loss_check = {'sharded_first_loss': first_loss, 'single_gpu_same_global_batch': ref, 'rel_diff': rel, 'ok': rel <= 1e-3}
+            del model1
+            torch.cuda.empty_cache()
+            if not loss_check['ok']:
+                raise SystemExit('multi-GPU loss check failed: %r' % (loss_check,))
+        dist.barrier()
+
+    t = torch.tensor([ms_total, ms_e2e, ms_eager], dtype=torch.float64, device=dev)
     if acc.distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_graph = float(t[0]), float(t[1]), float(t[2])
+    ms_total, ms_e2e, ms_eager = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         return
     hbm_peak, tc_peak, peak_kind = measured_peaks()
     samples = B * world * args.steps
     value = samples / (ms_total / 1e3)
-    algo_bytes = B * (1 + K) * d * 4                     # target/negative rows read once by the fused score kernel
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed `ncu --set full` capture
-    # (profiles/r01d_full_captures.csv: 542.5 MB + 10.7 MB); only known for the default workload on one GPU
-    traffic = 553.2e6 if (args.workload == DEFAULT_WORKLOAD and world == 1) else None
-    k_ms = statistics.mean(kernel_ms) if kernel_ms else float('nan')
-    achieved = algo_bytes / (k_ms / 1e3) / 1e9
+    traffic = ncu_traffic(name, world)
+
+    def hbm_entry(kname, label, ms, algo_bytes, note):
+        ach = algo_bytes / (ms / 1e3) / 1e9 if ms else None
+        return {'kernel': label, 'entry_point': kname, 'bound': 'hbm', 'ms_per_step': round(ms, 4), 'share_of_step': round(ms / (ms_eager / n_prof), 4),
+                'algorithmic_bytes_per_step': int(algo_bytes), 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': ach / hbm_peak if ach else None, 'traffic': traffic.get(kname), 'note': note}
+
+    kernels = []
+    score_name = 'ur_score_loss_fwd_bwd_f32' if world == 1 else 'ur_score_partial_f32'
+    # target/negative rows read once by the fused score kernel (per rank: 1/W of W batches' rows when sharded)
+    algo_score = B * (1 + K) * d * 4
+    if score_name in breakdown:
+        kernels.append(hbm_entry(score_name, 'fused gather+dot+loss+grad (score kernel)' if world == 1 else
+                                 'owner-side gather+dot+partial softmax (row-sharded table)', breakdown[score_name], algo_score,
+                                 '(1+K)*d*4 bytes per sample'))
+    if 'ur_rowlist_apply_f32' in breakdown and n_uniq:
+        rows = sum(n_uniq.values())
+        kernels.append(hbm_entry('ur_rowlist_apply_f32', 'row-sparse Adam (gradient reduce + update in place)', breakdown['ur_rowlist_apply_f32'],
+                                 rows * d * 4 * 6 + (B * L * d * 4 if L and w['model'] in ('SASRec', 'GRU') else 0),
+                                 '6*d*4 bytes per touched row (param, m, v read + written) + history gradient rows; %d unique rows' % rows))
+    if 'ur_pool_sum_fwd_f32' in breakdown:
+        kernels.append(hbm_entry('ur_pool_sum_fwd_f32', 'sum-pool tower gather-reduce', breakdown['ur_pool_sum_fwd_f32'],
+                                 live_hist_rows * d * 4, 'history rows read once: %d live rows per step x d*4 bytes' % live_hist_rows))
+    gemm_ms = sum(v for k, v in breakdown.items() if k.startswith('ur_gemm'))
+    if gemm_ms > 0:
+        flops_exec = sum(g['flops'] * (live_frac if g['live'] else 1.0) for g in gemm_log) / n_prof
+        bytes_exec = sum(g['bytes'] * (live_frac if g['live'] else 1.0) for g in gemm_log) / n_prof
+        if w['model'] == 'SASRec':
+            I = w['inner_size']
+            flops_nom = 3.0 * B * w['n_layers'] * L * (8 * d * d + 4 * d * I)
+        elif w['model'] == 'GRU':
+            h = w['hidden_size']
+            flops_nom = 3.0 * B * (L * 6 * h * (d + h) + 2 * h * d)
+        else:
+            flops_nom = flops_exec
+        kernels.append({'kernel': 'encoder GEMM family (tcgen05 / SIMT)', 'entry_point': 'ur_gemm_f32 + ur_gemm_fused_f32', 'bound': 'tensor',
+                        'ms_per_step': round(gemm_ms, 4), 'share_of_step': round(gemm_ms / (ms_eager / n_prof), 4),
+                        'flops_reference_nominal': flops_nom, 'flops_executed': flops_exec,
+                        'achieved': flops_nom / (gemm_ms / 1e3) / 1e12, 'achieved_executed': flops_exec / (gemm_ms / 1e3) / 1e12,
+                        'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': flops_nom / (gemm_ms / 1e3) / 1e12 / tc_peak,
+                        'frac_executed': flops_exec / (gemm_ms / 1e3) / 1e12 / tc_peak,
+                        'operand_bytes_per_step': int(bytes_exec), 'hbm_frac_of_operand_bytes': bytes_exec / (gemm_ms / 1e3) / 1e9 / hbm_peak,
+                        'note': 'nominal = the reference\'s 3 x forward flops over all B*L positions; executed = what the packed / trimmed '
+                                'encoder runs (live fraction %.3f); peak = measured sustained bf16 cuBLAS (MEASURED_PEAKS.json), the GEMMs '
+                                'run %s' % (live_frac, args.gemm_precision)})
+    attn_ms = breakdown.get('ur_attn_fwd_f32', 0.0) + breakdown.get('ur_attn_bwd_f32', 0.0)
+    if attn_ms > 0:
+        kernels.append({'kernel': 'fused attention fwd+bwd (SIMT fp32)', 'entry_point': 'ur_attn_fwd_f32 + ur_attn_bwd_f32', 'bound': 'latency',
+                        'ms_per_step': round(attn_ms, 4), 'share_of_step': round(attn_ms / (ms_eager / n_prof), 4)})
+    head = next((k for k in kernels if k['entry_point'] == score_name), None)
+    roofline = {'kernel': head['kernel'] if head else None, 'bound': 'hbm', 'achieved': head['achieved'] if head else None, 'peak': hbm_peak,
+                'unit': 'GB/s', 'frac': head['frac'] if head else None, 'traffic': head['traffic'] if head else None, 'peak_kind': peak_kind,
+                'algorithmic_bytes_per_launch': algo_score, 'kernel_ms': breakdown.get(score_name),
+                'timing': 'CUDA events around the C-ABI call on the launching stream, eager pass of the same %d steps' % n_prof,
+                'dominant_by_time': max(kernels, key=lambda k: k['ms_per_step'])['kernel'] if kernels else None, 'kernels': kernels}
     line = {
         'metric': 'training samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak' if 'global_B' not in w else 'strong',
         'vs_baseline': None, 'dtype': 'tf32' if args.gemm_precision == 'tf32' else 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'seq_len': L, 'n_items': w['n_items'],
-                   'n_neg': K, 'optimizer': 'adam: row-sparse (lazy) on tables, flat dense on encoder', 'dropout': 0.0,
-                   'gemm_precision': args.gemm_precision,
-                   'encoder': 'live positions only (pack_sequences=1) and last layer on B rows (trim_last_layer=1): dead rows of the '
-                              'reference computation are not computed, outputs and gradients identical (tests)',
-                   'l2': 'inputs larger than L2: %.1f GB table, random rows, %d rotating batches'
-                   % (w['n_items'] * d * 4 / 1e9, n_pool), 'parallelism': 'dp%d' % world, 'final_loss': final_loss},
+        'config': {'workload': name, 'model': w['model'], 'batch_per_gpu': B, 'global_batch': B * world, 'seq_len': L, 'n_items': w['n_items'],
+                   'n_neg': K, 'loss': w['loss_type'], 'optimizer': 'adam: row-sparse (lazy) on tables, flat dense on encoder; the CPU / eager-GPU '
+                   'baselines run the reference\'s dense Adam', 'dropout': args.dropout,
+                   'gemm_precision': args.gemm_precision, 'step': 'one CUDA graph per step' if graphed else 'eager launches',
+                   'encoder': 'live positions only (pack_sequences=1), last layer on B rows (trim_last_layer=1): dead rows of the reference '
+                              'computation are not computed, outputs and gradients identical (tests)' if w['model'] == 'SASRec' else w['model'],
+                   'l2': 'inputs larger than L2: %.1f GB table, random rows, %d rotating batches' % (w['n_items'] * d * 4 / 1e9, n_pool)
+                   if w['n_items'] * d * 4 > 126e6 else 'table fits L2 (%.1f MB): L2 flushed by the rotating %d batches only' % (w['n_items'] * d * 4 / 1e6, n_pool),
+                   'parallelism': 'dp%d%s' % (world, ' + row-sharded tables' if world > 1 else ''), 'first_loss': first_loss, 'final_loss': final_loss},
         'clocks': clk,
         'e2e': {'value': samples / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'value_cuda_graph': None if ms_graph != ms_graph else {'value': samples / (ms_graph / 1e3), 'unit': 'samples/s', 'ms_per_step': ms_graph / args.steps,
-                             'note': 'device-resident inputs, whole step replayed as one CUDA graph (the timed `value` region runs '
-                                     'eagerly so that the roofline kernel can be bracketed by CUDA events)'},
-        'roofline': {'kernel': 'score_loss_kernel (fused gather+dot+softmax+grad)' if world == 1 else
-                     'score_partial_kernel (owner-side gather+dot+partial softmax, row-sharded table)', 'bound': 'hbm', 'achieved': achieved,
-                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_kind': peak_kind,
-                     'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': k_ms},
+        'value_eager': {'value': B * world * n_prof / (ms_eager / 1e3), 'unit': 'samples/s', 'ms_per_step': ms_eager / n_prof,
+                        'note': 'same steps launched eagerly with CUDA events around every C-ABI call (the pass the roofline block is measured in)'},
+        'roofline': roofline,
+        'multi_gpu_loss_check': loss_check,
         'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
     }
+    if not args.no_eager_baseline and world == 1:
+        try:
+            line['gpu_eager_baseline'] = gpu_eager_baseline(dict(w, B=B), dev)
+        except RuntimeError as e:                     # dense [V,d] gradients + Adam state do not fit next to the resident model
+            line['gpu_eager_baseline'] = {'value': None, 'sample': 'failed: %s' % str(e)[:80]}
     if not args.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N=1 only
         from oracle import cpu_baseline
-        cfgo = dict(COMMON)
-        cfgo.update({k: v for k, v in w.items() if k not in ('K', 'B')})
+        wc, note = cpu_sample_workload(dict(w, B=B))
         try:
-            sps, ms, threads = cpu_baseline.time_steps(w['model'], cfgo, host[:2], steps=2, warmup=1)
+            cb = [synthetic_batch(wc, 100 + i) for i in range(2)]
+            sps, ms, threads = cpu_baseline.time_steps(wc['model'], oracle_cfg(wc), cb, steps=2, warmup=1)
             line['cpu_baseline'] = {'value': sps, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'ms_per_step': ms,
-                                    'sample': '2 timed steps of the full workload (B=%d, V=%d) after 1 warm-up, dense Adam' % (B, w['n_items'])}
+                                    'sample': '2 timed steps (B=%d, V=%d) after 1 warm-up, dense Adam; %s' % (wc['B'], wc['n_items'], note)}
         except (MemoryError, RuntimeError) as e:      # host RAM too small for dense grads + Adam state
             line['cpu_baseline'] = {'value': None, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
                                     'sample': 'failed: %s' % str(e)[:80]}

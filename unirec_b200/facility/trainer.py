@@ -54,9 +54,26 @@ class Trainer(object):
         self.optimizer = self._build_optimizer(config['optimizer'], self.model)
         self.scheduler = self._build_scheduler(config['scheduler'], config['scheduler_factor'])
         self.model, self.optimizer, self.scheduler = self.accelerator.prepare(self.model, self.optimizer, self.scheduler)
+        self._broadcast_replicated_params()
         self.evaluator = None
         self.user_history = None
         self.tb_logger = None
+
+    def _broadcast_replicated_params(self):
+        """Multi-process start: every replicated parameter takes rank 0's value (what DDP / accelerate.prepare do at
+        unirec/facility/trainer.py:67).  Row-sharded tables are per-rank data and stay."""
+        if not self.accelerator.distributed:
+            return
+        model = self.accelerator.unwrap_model(self.model)
+        eng = getattr(model, '_engine', None)
+        if eng is None or self.accelerator.device.type != 'cuda':
+            return
+        eng.ensure_ready()
+        if eng.flat is not None and eng.flat.size:
+            dist.broadcast(eng.flat.data, src=0)
+        if int(getattr(model, 'shard_world', 1)) <= 1:
+            for p in eng.table_params():
+                dist.broadcast(p.data, src=0)
 
     # ------------------------------------------------------------------ factories
     def _build_optimizer(self, opt_type, model):

@@ -45,6 +45,7 @@ LAUNCH_COUNT = 0
 TIMED_OP = None
 TIMED_EVENTS = []
 PROFILE = None
+GEMM_LOG = None       # bench.py: list of {'flops', 'bytes', 'live'} per GEMM launch (live = bounded by the device-side token count)
 
 
 def _call(name, *args):
@@ -236,6 +237,8 @@ def gemm(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None, ldc=N
         ldb = K if transB else N
     if ldc is None:
         ldc = N
+    if GEMM_LOG is not None:
+        GEMM_LOG.append({'flops': 2.0 * M * N * K, 'bytes': 4.0 * (M * K + K * N + M * N * (2 if preact is not None else 1)), 'live': False})
     _call('ur_gemm_f32', int(transA), int(transB), M, N, K, _f32(A), lda, _f32(B), ldb, _f32(C), ldc, _f32(bias),
           ACT_CODES[act], _f32(preact), ldp or N, int(accumulate), int(precision), _stream())
     return C
@@ -250,6 +253,9 @@ def gemm_fused(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None,
         ldb = K if transB else N
     if ldc is None:
         ldc = N
+    if GEMM_LOG is not None:
+        GEMM_LOG.append({'flops': 2.0 * M * N * K, 'live': rows_dev is not None,
+                         'bytes': 4.0 * (M * K + K * N + M * N * (1 + (preact is not None) + (dact is not None) + bool(accumulate)))})
     _call('ur_gemm_fused_f32', int(transA), int(transB), M, N, K, _f32(A), lda, _f32(B), ldb, _f32(C), ldc, _f32(bias),
           ACT_CODES[act], _f32(preact), ldp or N, int(accumulate), int(precision), _f32(dact), ldd or N, _f32(colsum),
           _i32(rows_dev), (2 if transA else 1) if rows_dev is not None else 0, _stream())
