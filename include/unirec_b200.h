@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UR_ABI_VERSION 2
+#define UR_ABI_VERSION 3
 
 enum { UR_LOSS_SOFTMAX = 0, UR_LOSS_BPR = 1 };
 enum { UR_ACT_NONE = 0, UR_ACT_SWISH = 1, UR_ACT_GELU = 2, UR_ACT_RELU = 3, UR_ACT_TANH = 4, UR_ACT_SIGMOID = 5 };
@@ -44,7 +44,8 @@ int ur_scatter_add_rows_f32(float* grad, int64_t n_rows, int d, const void* idx,
  * replaces: AvgHist.forward_user_emb unirec/model/sequential/avghist.py:34-42; SVDPlusPlus.forward_user_emb svdplusplus.py:31-39 */
 int ur_pool_sum_fwd_f32(const float* table, int d, const int32_t* item_seq, int64_t B, int L, const int64_t* item_seq_len,
                         float alpha, const float* user_table /*nullable*/, const int64_t* user_id, float* user_emb,
-                        float* coeff_out /*[B], nullable*/, void* stream);
+                        float* coeff_out /*[B], nullable*/, int world, int rank /*row-sharded tables: partial sum over the owned rows*/,
+                        void* stream);
 
 /* ---- K1+K3: Y = LayerNorm(table[item_seq] + pos[0..L-1]); saves per-row mean / rstd.
  * replaces: SASRec.forward_user_emb prologue, unirec/model/sequential/sasrec.py:60-69 */
@@ -175,8 +176,10 @@ int ur_loss_finish_f32(const float* loss_vec, int64_t B, const float* denom_dev 
  * u_begin_dev / u_end_dev: device-resident bounds of the slice of the unique-row list to update (default: all of it); rows are
  * appended in link order, so linking the history keys first makes [n_hist, n_uniq) the rows only the scorer touches -- those are
  * updated on a side stream while the encoder backward runs (small_ctas = 1: CTAs sized to co-reside with a GEMM CTA). */
+/* keys are masked with key_mask first (packed ids carry the label in bit 31); world > 1: keys are GLOBAL ids of a row-sharded table,
+ * only entries with key % world == rank are linked, under the local row key / world. */
 int ur_rowlist_link(int32_t* head, const void* keys, int idx_bits, int64_t n, int64_t entry_offset, int32_t* next, int32_t* uniq,
-                    int32_t* n_uniq, int64_t pad_id, void* stream);
+                    int32_t* n_uniq, int64_t pad_id, int world, int rank, int64_t key_mask, void* stream);
 int ur_rowlist_apply_f32(float* table, float* mom, float* var, int d, int32_t* head, const int32_t* next, const int32_t* uniq,
                          const int32_t* n_uniq, int64_t max_uniq, const float* src0, int64_t src0_group, const float* coef0,
                          int64_t coef0_group, int64_t n0, const float* src1, int64_t src1_group, const float* coef1,
@@ -236,16 +239,33 @@ int ur_rank_exclude_f32(const float* table_local, int d, const float* user_emb, 
 int ur_shard_gather_rows_f32(const float* table_local, int d, const void* idx, int idx_bits, int64_t n, int world, int rank,
                              float* out, void* stream);
 int ur_shard_localize(const void* idx, int idx_bits, int64_t n, int world, int rank, int64_t pad_id, int32_t* out, void* stream);
-/* one pass over the OWNED target rows of all S samples: state[s] = (max, sum exp, sum y*s, sum y, sum p*e [d], sum y*e [d]) */
-int ur_score_partial_f32(const float* table_local, int d, const float* user_emb, const int64_t* item_id, int64_t S, int N,
-                         const int32_t* label /*nullable*/, const float* item_bias /*nullable*/, const float* user_bias /*nullable*/,
-                         const int64_t* user_id, float tau, float score_clip, int world, int rank, float* z, float* state,
-                         void* stream);
-int ur_score_rescale_f32(float* state, const float* gmax, int64_t S, int d, void* stream);
-int ur_score_finish_f32(const float* state, const float* gmax, int64_t B, int d, float tau, const float* norm_dev, float* loss_vec,
-                        float* lse_ny, float* grad_user, void* stream);
-int ur_score_dscore_f32(const float* z, const int64_t* item_id, const int32_t* label /*nullable*/, const float* lse_ny, int64_t S,
-                        int N, int world, int rank, float tau, float score_clip, const float* norm_dev, float* dscore, void* stream);
+/* ---- owner-side scoring of the row-sharded target table (csrc/shard_ring.cu), "move queries, not rows".
+ * ur_pack_ids_i32: out[e] = id | (label > 0) << 31 (label NULL: positive in column 0) -- the ONE id tensor all-gathered per step.
+ * ur_score_partial_f32: per sample of any rank, one pass over the OWNED rows (cp.async.bulk ring, d = 128 / 256; generic fallback):
+ *   state[s] = (max, sum exp, sum y*s, sum y, sum p*e [d], sum y*e [d]), z[s, j] = raw score of owned entries.
+ * ur_score_merge_f32: home rank merges the W partial states of its B samples (states [W, B, 4+2d], one all-to-all) -> loss_vec, (lse, n_y),
+ *   dLoss/du.  ur_score_dscore_f32: owner, dLoss/d(dot) of owned entries.  norm_dev = global number of positive labels.
+ * replaces: forward_item_emb + InnerProductScorer + _predict_layer + softmax _cal_loss (recommender.py:55-96, reco_abc.py:260-265) under
+ *   DDP's replicated tables (trainer.py:67,346). */
+int ur_pack_ids_i32(const int64_t* item_id, const int32_t* label /*nullable*/, int64_t B, int N, int32_t* out, void* stream);
+int ur_count_positive_packed(const int32_t* ids_packed, int64_t n, float* out, void* stream);
+int ur_score_partial_f32(const float* table_local, int d, const float* user_emb, const int32_t* ids_packed, int64_t S, int N,
+                         const float* item_bias /*nullable*/, const float* user_bias /*nullable*/, const int64_t* user_id, float tau,
+                         float score_clip, int world, int rank, float* z, float* state, void* stream);
+int ur_score_merge_f32(const float* states, int world, int64_t B, int d, float tau, const float* norm_dev, float* loss_vec,
+                       float* lse_ny, float* grad_user, void* stream);
+int ur_score_dscore_f32(const float* z, const int32_t* ids_packed, const float* lse_ny, int64_t S, int N, int world, int rank,
+                        float tau, float score_clip, const float* norm_dev, float* dscore, void* stream);
+/* BPR on a row-sharded table (modules.py:15-21, reco_abc.py:252-255): owners score their entries (zeros elsewhere, summed by a
+ * reduce-scatter), the home rank forms loss and dLoss/d(dot) from the complete [B, N] scores (norm = S*K), owners form their part of
+ * dLoss/du (summed by a reduce-scatter). */
+int ur_shard_scores_f32(const float* table_local, int d, const float* user_emb, const int32_t* ids_packed, int64_t S, int N,
+                        const float* item_bias /*nullable*/, const float* user_bias /*nullable*/, const int64_t* user_id, float tau,
+                        int world, int rank, float* z, void* stream);
+int ur_bpr_from_scores_f32(const float* z, int64_t B, int N, float tau, float score_clip, float norm, float* loss_vec, float* dscore,
+                           float* scores /*nullable*/, void* stream);
+int ur_shard_grad_user_f32(const float* table_local, int d, const int32_t* ids_packed, const float* dscore, int64_t S, int N, int world,
+                           int rank, float* out, void* stream);
 
 #ifdef __cplusplus
 }

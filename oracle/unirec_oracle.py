@@ -120,7 +120,7 @@ def sasrec_attention_mask(item_seq, causal: bool, dtype):
     key_ok = (item_seq > 0).to(dtype)[:, None, None, :]
     if causal:
         L = item_seq.shape[1]
-        tri = torch.tril(torch.ones(L, L, dtype=dtype))[None, None]
+        tri = torch.tril(torch.ones(L, L, dtype=dtype, device=item_seq.device))[None, None]
         key_ok = key_ok * tri
     return (1.0 - key_ok) * -10000.0
 
@@ -193,7 +193,7 @@ def gru_user_emb(p, cfg, item_seq, drop=None):
     b_ih, b_hh = p['gru_layers.bias_ih_l0'], p['gru_layers.bias_hh_l0']
     H = w_hh.shape[1]
     B, L, _ = x.shape
-    h = torch.zeros(B, H, dtype=x.dtype)
+    h = torch.zeros(B, H, dtype=x.dtype, device=x.device)
     gi_all = linear(x, w_ih, b_ih)
     for t in range(L):
         gi = gi_all[:, t]

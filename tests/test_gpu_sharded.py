@@ -17,16 +17,24 @@ def _run(world, name, p2p=1):
            '127.0.0.1', '--master-port', str(29600 + world), os.path.join(HERE, 'dist_shard_check.py'), name, str(p2p)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0 and 'SHARD_OK' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
-    if world > 1 and not name.startswith('gru'):
+    if world > 1 and name.startswith('sasrec'):
         assert ('p2p=%d' % p2p) in res.stdout, res.stdout[-500:]
 
 
-@pytest.mark.parametrize('name', ['sasrec_softmax', 'sasrec_softmax_d128', 'gru_softmax_h32'])
+ALL_TOWERS = ['sasrec_softmax', 'sasrec_softmax_d128', 'gru_softmax_h32', 'gru_bpr', 'sasrec_bpr_nopos_bias', 'avghist_softmax',
+              'avghist_sym_bpr', 'svdpp_bpr', 'mf_bpr', 'mf_softmax_bias']
+
+
+@pytest.mark.parametrize('name', ALL_TOWERS)
 def test_sharded_engine_world1(name):
+    """The row-sharded engine with a single shard (table_shard_force): every tower x loss runs the owner-side kernels, the packed-id
+    path, the all-to-all merge / three-phase BPR and the sharded evaluation, and must equal the oracle step."""
     _run(1, name)
 
 
-@pytest.mark.parametrize('name,p2p', [('sasrec_softmax', 1), ('sasrec_softmax_d128', 1), ('sasrec_softmax', 0)])
+@pytest.mark.parametrize('name,p2p', [('sasrec_softmax', 1), ('sasrec_softmax_d128', 1), ('sasrec_softmax', 0), ('gru_bpr', 1),
+                                      ('sasrec_bpr_nopos_bias', 1), ('avghist_softmax', 1), ('avghist_sym_bpr', 1), ('svdpp_bpr', 1),
+                                      ('mf_bpr', 1), ('mf_softmax_bias', 1)])
 def test_sharded_engine_world2(name, p2p):
     """p2p=1: history rows / their gradients are read over NVLink through CUDA IPC mappings; p2p=0: NCCL reduce-scatter /
     all-gather of [W, B*L, d] buffers.  Both must reproduce the single-GPU golden step."""

@@ -17,7 +17,7 @@ SIGNATURES = {
     'ur_has_tensor_core_gemm': '',
     'ur_gather_rows_f32': 'plipilpp',
     'ur_scatter_add_rows_f32': 'plipilplpllp',
-    'ur_pool_sum_fwd_f32': 'piplipfppppp',
+    'ur_pool_sum_fwd_f32': 'piplipfpppp' + 'ii' + 'p',
     'ur_seq_prep_ln_fwd_f32': 'ppppfpliippp' + 'pp' + 'pi' + 'pfi' + 'p',
     'ur_seq_prep_ln_bwd_f32': 'pppplii' + 'ppp' + 'pppp' + 'p' + 'pi' + 'pfi' + 'p',
     'ur_add_ln_fwd_f32': 'plplppflipl' + 'pp' + 'p' + 'pfipll' + 'p',
@@ -42,7 +42,7 @@ SIGNATURES = {
     'ur_score_loss_fwd_bwd_f32': 'pipplipppp' + 'ffipf' + 'pppp' + 'p',
     'ur_count_positive_i32': 'plpp',
     'ur_loss_finish_f32': 'plpfppp',
-    'ur_rowlist_link': 'ppillpppl' + 'p',
+    'ur_rowlist_link': 'ppillpppl' + 'iil' + 'p',
     'ur_rowlist_apply_f32': 'pppi' + 'pppp' + 'l' + 'plpl' + 'l' + 'plpl' + 'i' + 'fffff' + 'ppp' + 'p' + 'ppi' + 'pl' + 'p',
     'ur_ipc_export': 'ppp',
     'ur_ipc_open': 'plp',
@@ -56,10 +56,14 @@ SIGNATURES = {
     'ur_rank_exclude_f32': 'piplpppppfiipplpp',
     'ur_shard_gather_rows_f32': 'pipiliipp',
     'ur_shard_localize': 'piliilpp',
-    'ur_score_partial_f32': 'pippli' + 'pppp' + 'ffii' + 'ppp',
-    'ur_score_rescale_f32': 'pplip',
-    'ur_score_finish_f32': 'pplifpppp' + 'p',
-    'ur_score_dscore_f32': 'pppplii' + 'iffpp' + 'p',
+    'ur_pack_ids_i32': 'pplipp',
+    'ur_count_positive_packed': 'plpp',
+    'ur_score_partial_f32': 'pippli' + 'ppp' + 'ffii' + 'ppp',
+    'ur_score_merge_f32': 'pilifpppp' + 'p',
+    'ur_score_dscore_f32': 'ppplii' + 'iffpp' + 'p',
+    'ur_shard_scores_f32': 'pippli' + 'ppp' + 'fii' + 'pp',
+    'ur_bpr_from_scores_f32': 'plifffppp' + 'p',
+    'ur_shard_grad_user_f32': 'pippliiipp',
 }
 
 _KIND = {'p': _P, 'i': _I, 'l': _L, 'f': _F}

@@ -66,7 +66,9 @@ template <int D4>   // d / 4
 __global__ void __launch_bounds__(128) pool_sum_kernel(const float4* __restrict__ E, const int32_t* __restrict__ seq, int L,
                                                        const int64_t* __restrict__ seq_len, float alpha,
                                                        const float4* __restrict__ U, const int64_t* __restrict__ user_id,
-                                                       float4* __restrict__ out, float* __restrict__ coeff_out) {
+                                                       float4* __restrict__ out, float* __restrict__ coeff_out, int W, int r) {
+    // W > 1: E / U are the row shards of rank r (rows id % W == r at local index id / W); rows of other ranks contribute nothing
+    // here -- the per-rank partial sums are added by a reduce-scatter (sharding.py)
     constexpr int LPR = D4 < 32 ? D4 : 32;      // lanes per row
     constexpr int VPL = D4 / LPR;               // float4 per lane
     constexpr int RPW = 32 / LPR;               // rows per warp per step
@@ -84,11 +86,11 @@ __global__ void __launch_bounds__(128) pool_sum_kernel(const float4* __restrict_
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             int l = l0 + u * rows_per_step + warp * RPW + sub;
-            ok[u] = l < L;
-            int32_t id = ok[u] ? __ldg(s + l) : 0;   // padding id 0 is gathered like any row (it holds zeros)
+            int32_t id = l < L ? __ldg(s + l) : 0;
+            ok[u] = id > 0 && (id % W) == r;          // the padding row holds zeros: skipped (adds nothing)
 #pragma unroll
             for (int v = 0; v < VPL; ++v)
-                if (ok[u]) t[u][v] = ldg_stream(E + (int64_t)id * D4 + v * LPR + col);
+                if (ok[u]) t[u][v] = ldg_stream(E + (int64_t)(id / W) * D4 + v * LPR + col);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -116,10 +118,12 @@ __global__ void __launch_bounds__(128) pool_sum_kernel(const float4* __restrict_
     const float cf = powf((float)(seq_len[b] + 1), -alpha);
     if (threadIdx.x == 0 && coeff_out) coeff_out[b] = cf;
     for (int c = threadIdx.x; c < D4; c += blockDim.x) {
-        float4 r = f4_add(f4_add(sm[0][c], sm[1][c]), f4_add(sm[2][c], sm[3][c]));
-        r = f4_scale(r, cf);
-        if (U) r = f4_add(r, __ldg(U + user_id[b] * D4 + c));
-        out[(int64_t)b * D4 + c] = r;
+        float4 o = f4_scale(f4_add(f4_add(sm[0][c], sm[1][c]), f4_add(sm[2][c], sm[3][c])), cf);
+        if (U) {
+            const int64_t uid = user_id[b];
+            if (uid % W == r) o = f4_add(o, __ldg(U + (uid / W) * D4 + c));
+        }
+        out[(int64_t)b * D4 + c] = o;
     }
 }
 
@@ -159,7 +163,8 @@ int ur_scatter_add_rows_f32(float* grad, int64_t n_rows, int d, const void* idx,
 
 int ur_pool_sum_fwd_f32(const float* table, int d, const int32_t* item_seq, int64_t B, int L, const int64_t* item_seq_len,
                         float alpha, const float* user_table, const int64_t* user_id, float* user_emb, float* coeff_out,
-                        void* stream) {
+                        int world, int rank, void* stream) {
+    if (world < 1 || rank < 0 || rank >= world) return UR_ERR_BAD_ARG;
     if (B == 0) return UR_OK;
     auto E = reinterpret_cast<const float4*>(table);
     auto U = reinterpret_cast<const float4*>(user_table);
@@ -168,7 +173,7 @@ int ur_pool_sum_fwd_f32(const float* table, int d, const int32_t* item_seq, int6
     switch (d) {
 #define UR_CASE(D)                                                                                                         \
     case D:                                                                                                                \
-        ur::pool_sum_kernel<D / 4><<<(unsigned)B, 128, 0, st>>>(E, item_seq, L, item_seq_len, alpha, U, user_id, O, coeff_out); \
+        ur::pool_sum_kernel<D / 4><<<(unsigned)B, 128, 0, st>>>(E, item_seq, L, item_seq_len, alpha, U, user_id, O, coeff_out, world, rank); \
         break;
         UR_CASE(16) UR_CASE(32) UR_CASE(64) UR_CASE(128) UR_CASE(256) UR_CASE(512)
 #undef UR_CASE

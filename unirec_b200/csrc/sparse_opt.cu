@@ -24,7 +24,8 @@ struct RowSource {
 
 __global__ void __launch_bounds__(256) rowlist_link_kernel(int32_t* __restrict__ head, const void* __restrict__ keys, int idx64,
                                                            int64_t n, int32_t entry_offset, int32_t* __restrict__ next,
-                                                           int32_t* __restrict__ uniq, int32_t* __restrict__ n_uniq, int64_t pad_id) {
+                                                           int32_t* __restrict__ uniq, int32_t* __restrict__ n_uniq, int64_t pad_id,
+                                                           int W, int r, int64_t key_mask) {
     // The unique-row list is appended through ONE global counter.  Same-address atomics retire at ~3 ns each, so a warp-level
     // append (33 K atomics for 1.05 M entries) cost ~100 us; the append is aggregated per CTA instead (one atomic per 256 entries).
     __shared__ int warp_cnt[8];
@@ -35,8 +36,12 @@ __global__ void __launch_bounds__(256) rowlist_link_kernel(int32_t* __restrict__
         bool first = false;
         int64_t id = pad_id;
         if (e < n) {
-            id = load_index(keys, idx64, e);
-            if (id != pad_id) {
+            // keys may carry flag bits (packed ids: label in bit 31) and, for a row-sharded table, be GLOBAL ids: only the entries
+            // this rank owns are linked, under their local row id / W
+            id = load_index(keys, idx64, e) & key_mask;
+            bool live = id != pad_id;
+            if (live && W > 1) { live = (id % W) == r; id /= W; }
+            if (live) {
                 const int32_t prev = atomicExch(head + id, entry_offset + (int32_t)e);
                 next[entry_offset + e] = prev;
                 first = prev < 0;
@@ -229,15 +234,16 @@ __global__ void step_advance_kernel(int32_t* step, const int32_t* skip_flag) {
 extern "C" {
 
 int ur_rowlist_link(int32_t* head, const void* keys, int idx_bits, int64_t n, int64_t entry_offset, int32_t* next, int32_t* uniq,
-                    int32_t* n_uniq, int64_t pad_id, void* stream) {
+                    int32_t* n_uniq, int64_t pad_id, int world, int rank, int64_t key_mask, void* stream) {
     if (idx_bits != 32 && idx_bits != 64) return UR_ERR_BAD_ARG;
+    if (world < 1 || rank < 0 || rank >= world) return UR_ERR_BAD_ARG;
     if (entry_offset + n >= (int64_t)1 << 31) return UR_ERR_UNSUPPORTED;
     if (n == 0) return UR_OK;
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)ur::kNumSMs * 8;
     if (blocks > cap) blocks = cap;
     ur::rowlist_link_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(head, keys, idx_bits == 64, n, (int32_t)entry_offset,
-                                                                                next, uniq, n_uniq, pad_id);
+                                                                                next, uniq, n_uniq, pad_id, world, rank, key_mask);
     UR_RETURN_LAST_ERROR();
 }
 

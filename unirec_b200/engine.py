@@ -90,7 +90,8 @@ class RowGrad:
         self.early = False         # this step's lists were linked ahead of the backward pass (Engine._early_link)
         self.specs = []            # list of (keys, src, src_group, coef, coef_group)
         self.linked = False
-        self.pad_id = 0            # key value that is skipped (global padding id; -1 for localized shard keys)
+        self.pad_id = 0            # key value that is skipped (the padding id)
+        self.shard = (1, 0)        # (world, rank): keys are global ids of a row-sharded table, only owned entries are linked
 
     def reset(self):
         self.specs = []
@@ -112,13 +113,14 @@ class RowGrad:
             self.n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
             self.n_hist = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def add(self, keys, src, src_group=1, coef=None, coef_group=1, parts=None):
-        """parts = (int64 device tensor of peer pointers, rows per part): the source rows live in per-rank buffers (sharding.py)."""
+    def add(self, keys, src, src_group=1, coef=None, coef_group=1, parts=None, key_mask=-1):
+        """parts = (int64 device tensor of peer pointers, rows per part): the source rows live in per-rank buffers (sharding.py);
+        key_mask strips the flag bits of packed ids (ops.pack_ids)."""
         if len(self.specs) >= 2:
             raise RuntimeError('a table takes at most two gradient sources per step')
         if parts is not None and not self.specs:
             raise RuntimeError('a multi-part source must be the second gradient source of a table')
-        self.specs.append((keys, src, int(src_group), coef, int(coef_group), parts))
+        self.specs.append((keys, src, int(src_group), coef, int(coef_group), parts, int(key_mask)))
 
     def n_entries(self):
         return sum(k.numel() for k, *_ in self.specs)
@@ -130,18 +132,21 @@ class RowGrad:
         self.prepare(self.n_entries())
         self.n_uniq.zero_()
         off = 0
-        for keys, *_ in self.specs:
-            ops.rowlist_link(self.head, keys, off, self.next, self.uniq, self.n_uniq, pad_id=self.pad_id)
+        for keys, *rest in self.specs:
+            ops.rowlist_link(self.head, keys, off, self.next, self.uniq, self.n_uniq, pad_id=self.pad_id, world=self.shard[0],
+                             rank=self.shard[1], key_mask=rest[-1])
             off += keys.numel()
         self.linked = True
 
     def sources(self):
-        return [(src, sg, coef, cg, keys.numel(), parts) for keys, src, sg, coef, cg, parts in self.specs]
+        return [(src, sg, coef, cg, keys.numel(), parts) for keys, src, sg, coef, cg, parts, _mask in self.specs]
 
     def to_dense(self):
         """Exact-dense mode: materialise the [V,d] gradient the reference's autograd would produce."""
         g = torch.zeros_like(self.param.data)
-        for keys, src, sg, coef, cg, parts in self.specs:
+        if self.shard[0] > 1:
+            raise RuntimeError('dense table gradients (table_update: dense) are not available with row-sharded tables')
+        for keys, src, sg, coef, cg, parts, _mask in self.specs:
             if parts is not None:
                 raise RuntimeError('dense table gradients are not available with peer-memory gradient sources')
             ops.scatter_add_rows(g, keys, src, sg, coef, cg, pad_id=self.pad_id)
@@ -519,28 +524,10 @@ class PoolTower:
         return []
 
     def forward(self, item_seq=None, item_seq_len=None, user_id=None, save=True, **_):
-        eng, ws = self.eng, self.eng.ws
-        utable = eng.model.user_embedding.weight if self.use_user else None
-        if not self.use_seq:
-            B = user_id.shape[0]
-            user = ws.get('user_emb', (B, self.d))
-            ops.gather_rows(utable.data, user_id, out=user)
-        else:
-            B = item_seq.shape[0]
-            user = ws.get('user_emb', (B, self.d))
-            self.coeff = ws.get('pool_coeff', (B,))
-            ops.pool_sum_fwd(eng.table_for_seq().data, item_seq, item_seq_len, self.alpha,
-                             utable.data if utable is not None else None, user_id, out=user, coeff_out=self.coeff)
-        self.item_seq, self.user_id = item_seq, user_id
-        return user
+        return self.eng.pool_forward(item_seq, item_seq_len, user_id, self.use_seq, self.use_user, self.alpha)
 
     def backward(self, d_user):
-        eng = self.eng
-        if self.use_seq:
-            L = self.item_seq.shape[1]
-            eng.rowgrad(eng.table_for_seq()).add(self.item_seq, d_user, L, self.coeff, L)
-        if self.use_user:
-            eng.rowgrad(eng.model.user_embedding.weight).add(self.user_id, d_user, 1, None, 1)
+        self.eng.pool_backward(d_user, self.use_seq, self.use_user)
 
 
 # ==================================================================================================
@@ -584,10 +571,15 @@ class Engine:
                 out.append(mod.weight)
         return out
 
+    def link_filter(self):
+        """(world, rank) of the row partition of the tables (keys of the row lists are global ids)."""
+        return 1, 0
+
     def rowgrad(self, param) -> RowGrad:
         rg = self._rowgrads.get(id(param))
         if rg is None:
             rg = self._rowgrads[id(param)] = RowGrad(param)
+            rg.shard = self.link_filter()
         return rg
 
     def rowgrads(self):
@@ -668,6 +660,32 @@ class Engine:
             self._ev_link.record(self._side)
         rg.linked = True
         rg.early = True
+
+    # ---- sum-pool tower hooks (overridden by the row-sharded engine) -----------------------------
+    def pool_forward(self, item_seq, item_seq_len, user_id, use_seq, use_user, alpha):
+        ws = self.ws
+        d = self.table_for_target().shape[1]
+        utable = self.model.user_embedding.weight if use_user else None
+        if not use_seq:
+            user = ws.get('user_emb', (user_id.shape[0], d))
+            ops.gather_rows(utable.data, user_id, out=user)
+            coeff = None
+        else:
+            B = item_seq.shape[0]
+            user = ws.get('user_emb', (B, d))
+            coeff = ws.get('pool_coeff', (B,))
+            ops.pool_sum_fwd(self.table_for_seq().data, item_seq, item_seq_len, alpha,
+                             utable.data if utable is not None else None, user_id, out=user, coeff_out=coeff)
+        self._pool_saved = (item_seq, coeff, user_id)
+        return user
+
+    def pool_backward(self, d_user, use_seq, use_user):
+        item_seq, coeff, user_id = self._pool_saved
+        if use_seq:
+            L = item_seq.shape[1]
+            self.rowgrad(self.table_for_seq()).add(item_seq, d_user, L, coeff, L)
+        if use_user:
+            self.rowgrad(self.model.user_embedding.weight).add(user_id, d_user, 1, None, 1)
 
     # ---- sequence-row hooks (overridden by the row-sharded engine) -------------------------------
     def seq_rows_source(self, item_seq):

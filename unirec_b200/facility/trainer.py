@@ -204,9 +204,13 @@ class Trainer(object):
         from unirec_b200.engine import Engine
         model = self.accelerator.unwrap_model(self.model)
         eng = getattr(model, '_engine', None)
-        if (not int(self.config.get('cuda_graph', 1)) or self.accelerator.distributed or type(eng) is not Engine
+        from unirec_b200.sharding import ShardedEngine
+        # the row-sharded step (NCCL collectives + peer-memory kernels) is captured too: `cuda_graph_sharded: 0` keeps it eager
+        sharded_ok = type(eng) is ShardedEngine and int(self.config.get('cuda_graph_sharded', 1))
+        if (not int(self.config.get('cuda_graph', 1)) or not (type(eng) is Engine or sharded_ok)
+                or (self.accelerator.distributed and not sharded_ok)
                 or not isinstance(self.optimizer, FusedOptimizer) and not isinstance(getattr(self.optimizer, 'optimizer', None), FusedOptimizer)
-                or ops.PROFILE is not None or ops.TIMED_OP is not None or eng.overlap_hook is not None):
+                or ops.PROFILE is not None or ops.TIMED_OP is not None or ops.TIMED_OPS is not None or eng.overlap_hook is not None):
             return None
         tensors = {k: v for k, v in samples.items() if torch.is_tensor(v)}
         if not tensors or any(not v.is_cuda for v in tensors.values()) or len(tensors) != len(samples):
@@ -287,8 +291,8 @@ class Trainer(object):
             for batch_idx, inter_data in enumerate(self.device_batches(train_data)):
                 samples = {k: inter_data[v] for k, v in key2index.items()}
                 loss = self.train_step(samples)
-                if self.accelerator.distributed:
-                    loss = self.accelerator.gather_for_metrics(loss).mean()
+                if self.accelerator.distributed and int(getattr(flag, 'world', 1)) <= 1:
+                    loss = self.accelerator.gather_for_metrics(loss).mean()     # (the row-sharded engine reports the global loss)
                 # NaN batches contribute nothing to the epoch loss (reference `continue`s before accumulating)
                 contrib = torch.where(flag.nan_flag[0] != 0, torch.zeros_like(loss), loss)
                 total = contrib if total is None else total + contrib

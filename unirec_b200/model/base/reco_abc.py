@@ -118,22 +118,29 @@ class AbstractRecommender(nn.Module):
         # `table_init_device: 1` (unirec_b200 addition, used by bench.py): the big tables are created and initialised directly in
         # HBM (a 50M x 128 table never exists in host memory); values then come from the device generator, not the reference's
         tdev = self.device if int(self.config.get('table_init_device', 0) or 0) and torch.device(self.device).type == 'cuda' else None
-        if self.config['has_user_emb']:
-            self.user_embedding = nn.Embedding(self.n_users, self.embedding_size, padding_idx=0, device=tdev)
-        # row-sharded item tables (multi-GPU): this rank stores rows {id : id % W == r}; the padding row lives on rank 0
+        # row-sharded tables (multi-GPU): this rank stores rows {id : id % W == r}; the padding row lives on rank 0
         W, r = self.shard_world, self.shard_rank
-        rows = (self.n_items - r + W - 1) // W
         self._chunked_table_init = (W > 1 or tdev is not None) and self.init_method == 'normal'
-        if self._chunked_table_init:
-            # no constructor draw for the shard; in host mode burn the n_items x d N(0,1) draws nn.Embedding's own reset_parameters
-            # makes in the unsharded model, so that the generator stays aligned with it (see _init_params)
-            self.item_embedding = nn.Embedding(rows, self.embedding_size, padding_idx=0 if r == 0 else None,
-                                               _weight=torch.empty(rows, self.embedding_size, device=tdev))
-            if tdev is None:
-                for c0 in range(0, self.n_items, 1 << 18):
-                    torch.empty(min(self.n_items, c0 + (1 << 18)) - c0, self.embedding_size).normal_()
-        else:
-            self.item_embedding = nn.Embedding(rows, self.embedding_size, padding_idx=0 if r == 0 else None, device=tdev)
+        self._table_rows = {}            # id(weight) -> full row count of a table created through _make_table
+
+        def _make_table(n_rows):
+            rows = (n_rows - r + W - 1) // W
+            if self._chunked_table_init:
+                # no constructor draw for the shard; in host mode burn the n_rows x d N(0,1) draws nn.Embedding's own reset_parameters
+                # makes in the unsharded model, so that the generator stays aligned with it (see _init_params)
+                emb = nn.Embedding(rows, self.embedding_size, padding_idx=0 if r == 0 else None,
+                                   _weight=torch.empty(rows, self.embedding_size, device=tdev))
+                if tdev is None:
+                    for c0 in range(0, n_rows, 1 << 18):
+                        torch.empty(min(n_rows, c0 + (1 << 18)) - c0, self.embedding_size).normal_()
+            else:
+                emb = nn.Embedding(rows, self.embedding_size, padding_idx=0 if r == 0 else None, device=tdev)
+            emb._ur_full_rows = n_rows
+            return emb
+
+        if self.config['has_user_emb']:
+            self.user_embedding = _make_table(self.n_users)
+        self.item_embedding = _make_table(self.n_items)
         self._define_model_layers()
         self._init_params()
 
@@ -143,13 +150,14 @@ class AbstractRecommender(nn.Module):
         W, r = self.shard_world, self.shard_rank
 
         def init_sharded_table(emb):
-            """Row shard of the table the UNSHARDED model would draw: the full [n_items, d] stream is generated in row chunks and
+            """Row shard of the table the UNSHARDED model would draw: the full [n_rows, d] stream is generated in row chunks and
             rows id % W == r are kept, so every rank consumes the same amount of the generator (the replicated encoder that
             follows is initialised identically on all ranks) and the W shards together equal the single-GPU initial table."""
             w = emb.weight.data
+            n_rows = emb._ur_full_rows
             chunk = 1 << 18
-            for c0 in range(0, self.n_items, chunk):
-                c1 = min(self.n_items, c0 + chunk)
+            for c0 in range(0, n_rows, chunk):
+                c1 = min(n_rows, c0 + chunk)
                 full = torch.empty(c1 - c0, w.shape[1], dtype=w.dtype, device=w.device).normal_(mean=mean, std=std)
                 first = (r - c0) % W                      # first row of the chunk owned by this rank
                 mine = full[first::W]
@@ -160,8 +168,7 @@ class AbstractRecommender(nn.Module):
 
         done = set()
         for _, module in self.named_children():
-            if (self._chunked_table_init and isinstance(module, nn.Embedding) and hasattr(self, 'item_embedding')
-                    and module.weight.shape == self.item_embedding.weight.shape and module is not getattr(self, 'user_embedding', None)):
+            if self._chunked_table_init and isinstance(module, nn.Embedding) and hasattr(module, '_ur_full_rows'):
                 if id(module.weight) not in done:
                     done.add(id(module.weight))
                     init_sharded_table(module)

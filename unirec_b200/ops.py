@@ -43,6 +43,7 @@ def _idx_bits(idx):
 # (TIMED_OP) or around every entry point (PROFILE dict).  All off by default.
 LAUNCH_COUNT = 0
 TIMED_OP = None
+TIMED_OPS = None      # bench.py: set of entry points bracketed by CUDA events -> TIMED_EVENTS gets (name, start, end)
 TIMED_EVENTS = []
 PROFILE = None
 GEMM_LOG = None       # bench.py: list of {'flops', 'bytes', 'live'} per GEMM launch (live = bounded by the device-side token count)
@@ -52,13 +53,15 @@ def _call(name, *args):
     global LAUNCH_COUNT
     LAUNCH_COUNT += 1
     fn = getattr(_cabi.lib(), name)
-    if PROFILE is not None or name == TIMED_OP:
+    if PROFILE is not None or name == TIMED_OP or (TIMED_OPS is not None and name in TIMED_OPS):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         rc = fn(*args)
         b.record()
         if name == TIMED_OP:
             TIMED_EVENTS.append((a, b))
+        elif TIMED_OPS is not None and name in TIMED_OPS:
+            TIMED_EVENTS.append((name, a, b))
         if PROFILE is not None:
             PROFILE.setdefault(name, []).append((a, b))
     else:
@@ -91,14 +94,14 @@ def scatter_add_rows(grad, idx, src, src_group=1, coef=None, coef_group=1, pad_i
     return grad
 
 
-def pool_sum_fwd(table, item_seq, item_seq_len, alpha, user_table=None, user_id=None, out=None, coeff_out=None):
+def pool_sum_fwd(table, item_seq, item_seq_len, alpha, user_table=None, user_id=None, out=None, coeff_out=None, world=1, rank=0):
     B, L = item_seq.shape
     d = table.shape[1]
     if out is None:
         out = torch.empty(B, d, dtype=torch.float32, device=table.device)
     _call('ur_pool_sum_fwd_f32', _f32(table), d, _ptr(item_seq, torch.int32), B, L, _ptr(item_seq_len, torch.int64),
           float(alpha), _f32(user_table), _ptr(user_id, torch.int64) if user_id is not None else None, _f32(out),
-          _f32(coeff_out), _stream())
+          _f32(coeff_out), int(world), int(rank), _stream())
     return out
 
 
@@ -329,9 +332,12 @@ def loss_finish(loss_vec, loss_out, denom_dev=None, denom_host=1.0, nan_flag=Non
 
 
 # ------------------------------------------------------------------ row-sparse optimizer
-def rowlist_link(head, keys, entry_offset, nxt, uniq, n_uniq, pad_id=0):
+def rowlist_link(head, keys, entry_offset, nxt, uniq, n_uniq, pad_id=0, world=1, rank=0, key_mask=-1):
+    """world > 1: `keys` are global ids of a row-sharded table (only owned entries are linked, under local rows); key_mask strips
+    flag bits of packed ids (ops.pack_ids)."""
     _call('ur_rowlist_link', _ptr(head, torch.int32), _ptr(keys), _idx_bits(keys), keys.numel(), entry_offset,
-          _ptr(nxt, torch.int32), _ptr(uniq, torch.int32), _ptr(n_uniq, torch.int32), pad_id, _stream())
+          _ptr(nxt, torch.int32), _ptr(uniq, torch.int32), _ptr(n_uniq, torch.int32), pad_id, int(world), int(rank), int(key_mask),
+          _stream())
 
 
 def rowlist_apply(table, mom, var, head, nxt, uniq, n_uniq, max_uniq, sources, mode, lr=0.0, beta1=0.9, beta2=0.999,
@@ -408,28 +414,58 @@ def shard_localize(idx, world, rank, out, pad_id=0):
     return out
 
 
-def score_partial(table_local, user_emb, item_id, world, rank, z, state, label=None, item_bias=None, user_bias=None,
-                  user_id=None, tau=1.0, score_clip=-1.0):
-    S, N = item_id.shape
-    _call('ur_score_partial_f32', _f32(table_local), table_local.shape[1], _f32(user_emb), _ptr(item_id, torch.int64), S, N,
-          _ptr(label, torch.int32) if label is not None else None, _f32(item_bias), _f32(user_bias),
-          _ptr(user_id, torch.int64) if user_id is not None else None, float(tau), float(score_clip), world, rank,
-          _f32(z), _f32(state), _stream())
+PACKED_ID_MASK = 0x7FFFFFFF
 
 
-def score_rescale(state, gmax, d):
-    _call('ur_score_rescale_f32', _f32(state), _f32(gmax), gmax.numel(), d, _stream())
+def pack_ids(item_id, label, out):
+    """out[e] = id | (label > 0) << 31 (int32): the one id tensor the row-sharded step all-gathers."""
+    B, N = item_id.shape
+    _call('ur_pack_ids_i32', _ptr(item_id, torch.int64), _ptr(label, torch.int32) if label is not None else None, B, N,
+          _ptr(out, torch.int32), _stream())
+    return out
 
 
-def score_finish(state, gmax, d, tau, norm_dev, loss_vec, lse_ny, grad_user):
-    _call('ur_score_finish_f32', _f32(state), _f32(gmax), gmax.numel(), d, float(tau), _f32(norm_dev), _f32(loss_vec),
-          _f32(lse_ny), _f32(grad_user), _stream())
+def count_positive_packed(ids, out):
+    _call('ur_count_positive_packed', _ptr(ids, torch.int32), ids.numel(), _f32(out), _stream())
+    return out
 
 
-def score_dscore(z, item_id, label, lse_ny, world, rank, tau, score_clip, norm_dev, dscore):
-    S, N = item_id.shape
-    _call('ur_score_dscore_f32', _f32(z), _ptr(item_id, torch.int64), _ptr(label, torch.int32) if label is not None else None,
-          _f32(lse_ny), S, N, world, rank, float(tau), float(score_clip), _f32(norm_dev), _f32(dscore), _stream())
+def score_partial(table_local, user_emb, ids, world, rank, z, state, item_bias=None, user_bias=None, user_id=None, tau=1.0,
+                  score_clip=-1.0):
+    S, N = ids.shape
+    _call('ur_score_partial_f32', _f32(table_local), table_local.shape[1], _f32(user_emb), _ptr(ids, torch.int32), S, N,
+          _f32(item_bias), _f32(user_bias), _ptr(user_id, torch.int64) if user_id is not None else None, float(tau),
+          float(score_clip), world, rank, _f32(z), _f32(state), _stream())
+
+
+def score_merge(states, world, B, d, tau, norm_dev, loss_vec, lse_ny, grad_user):
+    _call('ur_score_merge_f32', _f32(states), int(world), int(B), int(d), float(tau), _f32(norm_dev), _f32(loss_vec), _f32(lse_ny),
+          _f32(grad_user), _stream())
+
+
+def score_dscore(z, ids, lse_ny, world, rank, tau, score_clip, norm_dev, dscore):
+    S, N = ids.shape
+    _call('ur_score_dscore_f32', _f32(z), _ptr(ids, torch.int32), _f32(lse_ny), S, N, world, rank, float(tau), float(score_clip),
+          _f32(norm_dev), _f32(dscore), _stream())
+
+
+def shard_scores(table_local, user_emb, ids, world, rank, z, item_bias=None, user_bias=None, user_id=None, tau=1.0):
+    S, N = ids.shape
+    _call('ur_shard_scores_f32', _f32(table_local), table_local.shape[1], _f32(user_emb), _ptr(ids, torch.int32), S, N,
+          _f32(item_bias), _f32(user_bias), _ptr(user_id, torch.int64) if user_id is not None else None, float(tau), world, rank,
+          _f32(z), _stream())
+
+
+def bpr_from_scores(z, tau, score_clip, norm, loss_vec, dscore, scores=None):
+    B, N = z.shape
+    _call('ur_bpr_from_scores_f32', _f32(z), B, N, float(tau), float(score_clip), float(norm), _f32(loss_vec), _f32(dscore),
+          _f32(scores), _stream())
+
+
+def shard_grad_user(table_local, ids, dscore, world, rank, out):
+    S, N = ids.shape
+    _call('ur_shard_grad_user_f32', _f32(table_local), table_local.shape[1], _ptr(ids, torch.int32), _f32(dscore), S, N, world, rank,
+          _f32(out), _stream())
 
 
 # ------------------------------------------------------------------ one-vs-all ranking (evaluation, csrc/evalrank.cu)
