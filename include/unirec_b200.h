@@ -156,6 +156,15 @@ int ur_gru_gate_fwd_f32(const float* gi, int64_t ld_gi, const float* gh, const f
 int ur_gru_gate_bwd_f32(const float* dh, const float* save, const float* h_prev, float* dgi, int64_t ld_dgi, float* dgh,
                         float* dh_prev, int64_t B, int H, void* stream);
 
+/* Persistent recurrence: ONE launch per direction runs all L steps (a CTA owns 16 batch rows for the whole sequence, hidden tile in
+ * shared memory, W_hh streamed from L2; csrc/gru.cu).  gi / dgi [B, L, 3H] batch-major; hs [L+1, B, H], hs[0] = initial state; save
+ * [L, B, 4H]; whh_t = W_hh^T [H, 3H]; dgh_all [L, B, 3H] feeds the W_hh / b_hh gradient reductions.  H % 32 == 0, H <= 768 (stock GRU.yaml: 768).
+ * replaces: nn.GRU (cuDNN RNN / ATen step loop) unirec/model/sequential/gru.py:30 and its autograd */
+int ur_gru_seq_fwd_f32(const float* gi, const float* whh_t, const float* b_hh, float* hs, float* save, int64_t B, int64_t L, int H,
+                       void* stream);
+int ur_gru_seq_bwd_f32(const float* dh_last, const float* save, const float* hs, const float* whh, float* dgi, float* dgh_all, int64_t B,
+                       int64_t L, int H, void* stream);
+
 /* ---- K8: fused target/negative gather + scores + bias/tau/clamp + loss + dLoss/dscore + dLoss/du, one pass over the rows.
  * replaces: forward_item_emb + InnerProductScorer + _predict_layer + _cal_loss and their autograd:
  *   unirec/model/base/recommender.py:55-59,66-96; unirec/model/modules.py:15-21,45-67; unirec/model/base/reco_abc.py:252-265

@@ -59,6 +59,9 @@ CASES = {
                               hidden_dropout_prob=0.5, attn_dropout_prob=0.5, drop_step=11),
     'gru_bpr_drop': dict(model='GRU', n_items=123, n_users=19, embedding_size=32, hidden_size=64, max_seq_len=7, loss_type='bpr',
                          K=5, B=6, init_std=0.3, dropout_prob=0.4, drop_step=3),
+    # BASELINE config c3 shape of the recurrence (d = h = 256, L = 100) on a small catalogue: pins the persistent GRU kernel
+    'gru_d256_h256_L100': dict(model='GRU', n_items=301, n_users=19, embedding_size=256, hidden_size=256, max_seq_len=100,
+                               loss_type='bpr', K=5, B=3, init_std=0.1),
     'gru_bpr': dict(model='GRU', n_items=123, n_users=19, embedding_size=32, hidden_size=64,
                     max_seq_len=7, loss_type='bpr', K=5, B=6, init_std=0.3),
     'gru_softmax_h32': dict(model='GRU', n_items=99, n_users=19, embedding_size=32, hidden_size=32,

@@ -38,6 +38,8 @@ SIGNATURES = {
     'ur_attn_fwd_f32': 'ppliiiiipp' + 'ppp' + 'pfi' + 'p',
     'ur_attn_bwd_f32': 'ppliiiii' + 'pppp' + 'pppp' + 'pfi' + 'p',
     'ur_gru_gate_fwd_f32': 'plppppli' + 'p',
+    'ur_gru_seq_fwd_f32': 'ppppplli' + 'p',
+    'ur_gru_seq_bwd_f32': 'ppppppll' + 'i' + 'p',
     'ur_gru_gate_bwd_f32': 'pppplppli' + 'p',
     'ur_score_loss_fwd_bwd_f32': 'pipplipppp' + 'ffipf' + 'pppp' + 'p',
     'ur_count_positive_i32': 'plpp',

@@ -449,6 +449,7 @@ class GRUTower:
         self.eng = eng
         self.d = int(cfg['embedding_size'])
         self.Hd = int(cfg.get('hidden_size', self.d))
+        self.persistent = bool(int(cfg.get('gru_persistent', 1)))   # 0: one GEMM + gate kernel per time step (A/B testing)
         self.p_emb = float(cfg.get('dropout_prob', 0) or 0)        # nn.Dropout on the gathered rows, gru.py:29
         if not 0.0 <= self.p_emb < 1.0:
             raise ValueError('dropout_prob must lie in [0, 1), got %r' % (self.p_emb,))
@@ -474,9 +475,14 @@ class GRUTower:
         save_g = ws.get('gru_save', (L, B, 4 * Hd))
         gh = ws.get('gru_gh', (B, 3 * Hd))
         w_hh, b_hh = fp.p('gru_layers.weight_hh_l0'), fp.p('gru_layers.bias_hh_l0')
-        for t in range(L):
-            _lin_fwd(hs[t], B, Hd, w_hh, b_hh, 3 * Hd, gh, prec=prec)
-            ops.gru_gate_fwd(gi[t:], L * 3 * Hd, gh, hs[t], hs[t + 1], save_g[t], B, Hd)
+        if self.persistent and Hd % 32 == 0 and Hd <= 768:
+            # one launch for all L steps: W_hh^T streamed from L2, hidden tile resident in shared memory (csrc/gru.cu)
+            whh_t = ops.transpose(w_hh, ws.get('gru_whh_t', (Hd, 3 * Hd)))
+            ops.gru_seq_fwd(gi, whh_t, b_hh, hs, save_g, B, L, Hd)
+        else:
+            for t in range(L):
+                _lin_fwd(hs[t], B, Hd, w_hh, b_hh, 3 * Hd, gh, prec=prec)
+                ops.gru_gate_fwd(gi[t:], L * 3 * Hd, gh, hs[t], hs[t + 1], save_g[t], B, Hd)
         user = ws.get('user_emb', (B, d))
         _lin_fwd(hs[L], B, Hd, fp.p('dense.weight'), fp.p('dense.bias'), d, user, prec=prec)
         self.item_seq, self.x, self.hs, self.save_g = item_seq, x, hs, save_g
@@ -493,11 +499,14 @@ class GRUTower:
         dgi = ws.get('gru_dgi', (B * L, 3 * Hd))
         dgh_all = ws.get('gru_dgh', (L, B, 3 * Hd))
         w_hh = fp.p('gru_layers.weight_hh_l0')
-        for t in reversed(range(L)):
-            dh_prev = ws.get('gru_dh_b' if (L - t) % 2 else 'gru_dh_a', (B, Hd))
-            ops.gru_gate_bwd(dh, save_g[t], hs[t], dgi[t:], L * 3 * Hd, dgh_all[t], dh_prev, B, Hd)
-            ops.gemm(dgh_all[t], w_hh, dh_prev, B, Hd, 3 * Hd, accumulate=True, precision=prec)
-            dh = dh_prev
+        if self.persistent and Hd % 32 == 0 and Hd <= 768:
+            ops.gru_seq_bwd(dh, save_g, hs, w_hh, dgi, dgh_all, B, L, Hd)
+        else:
+            for t in reversed(range(L)):
+                dh_prev = ws.get('gru_dh_b' if (L - t) % 2 else 'gru_dh_a', (B, Hd))
+                ops.gru_gate_bwd(dh, save_g[t], hs[t], dgi[t:], L * 3 * Hd, dgh_all[t], dh_prev, B, Hd)
+                ops.gemm(dgh_all[t], w_hh, dh_prev, B, Hd, 3 * Hd, accumulate=True, precision=prec)
+                dh = dh_prev
         # weight gradients over all steps at once
         ops.gemm(dgh_all, hs, fp.g('gru_layers.weight_hh_l0'), 3 * Hd, Hd, L * B, transA=True, lda=3 * Hd, ldb=Hd,
                  accumulate=True, precision=prec)

@@ -309,6 +309,14 @@ def gru_gate_bwd(dh, save, h_prev, dgi, ld_dgi, dgh, dh_prev, B, H):
           _stream())
 
 
+def gru_seq_fwd(gi, whh_t, b_hh, hs, save, B, L, H):
+    _call('ur_gru_seq_fwd_f32', _f32(gi), _f32(whh_t), _f32(b_hh), _f32(hs), _f32(save), B, L, H, _stream())
+
+
+def gru_seq_bwd(dh_last, save, hs, whh, dgi, dgh_all, B, L, H):
+    _call('ur_gru_seq_bwd_f32', _f32(dh_last), _f32(save), _f32(hs), _f32(whh), _f32(dgi), _f32(dgh_all), B, L, H, _stream())
+
+
 # ------------------------------------------------------------------ fused score + loss
 def score_loss(table, user_emb, item_id, loss_type, label=None, item_bias=None, user_bias=None, user_id=None, tau=1.0,
                score_clip=-1.0, norm_dev=None, norm_host=1.0, scores=None, loss_vec=None, dscore=None, grad_user=None):
