@@ -385,3 +385,22 @@ def test_frozen_parameters_do_not_move():
     assert not torch.equal(after['position_embedding.weight'], before['position_embedding.weight'])
     head = model._engine.rowgrad(model.item_embedding.weight).head
     assert head is None or int((head != -1).sum()) == 0
+
+
+@pytest.mark.parametrize('name', ['gru_bpr', 'gru_softmax_h32', 'gru_d256_h256_L100', 'gru_bpr_drop'])
+def test_gru_persistent_recurrence_matches_reference(name):
+    """gru_persistent=1: the whole recurrence in one launch per direction (csrc/gru.cu) reproduces the reference goldens (forward,
+    dense gradients), incl. the BASELINE c3 recurrence shape d = h = 256, L = 100."""
+    g = Golden(name)
+    model, _ = cuda_model(g, table_update='dense', gru_persistent=1)
+    model.train()
+    g.arm(model)
+    loss, scores, user_emb, _ = model(**to_dev(g.fwd_batch()), return_loss_only=False)
+    assert abs(float(loss) - float(g.loss)) <= TOL * abs(float(g.loss))
+    assert rel_err(scores.cpu(), g.scores) < TOL and rel_err(user_emb.cpu(), g.user_emb) < TOL
+    loss.backward()
+    scale = max(float(v.abs().max()) for v in g.grads.values())
+    for k, p in model.named_parameters():
+        ref = g.grads[k]
+        err = float((p.grad.cpu().double() - ref.double()).abs().max())
+        assert err <= TOL * max(float(ref.abs().max()), 1e-2 * scale), (k, err)

@@ -449,7 +449,8 @@ class GRUTower:
         self.eng = eng
         self.d = int(cfg['embedding_size'])
         self.Hd = int(cfg.get('hidden_size', self.d))
-        self.persistent = bool(int(cfg.get('gru_persistent', 1)))   # 0: one GEMM + gate kernel per time step (A/B testing)
+        self.persistent = bool(int(cfg.get('gru_persistent', 0)))   # 1: one launch per direction for all L steps (csrc/gru.cu); 0: one
+                                                                    # tcgen05 GEMM + gate kernel per time step inside the step's CUDA graph (faster at c3 today)
         self.p_emb = float(cfg.get('dropout_prob', 0) or 0)        # nn.Dropout on the gathered rows, gru.py:29
         if not 0.0 <= self.p_emb < 1.0:
             raise ValueError('dropout_prob must lie in [0, 1), got %r' % (self.p_emb,))
