@@ -109,18 +109,52 @@ def ncu_traffic(workload, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  In-process NVML polling every few
+    milliseconds on a helper thread (the timed regions last 40-100 ms: an nvidia-smi child process does not even start in that time,
+    and one nvidia-smi loop per rank slowed the 8-GPU step by ~20%); falls back to `nvidia-smi -lms` when NVML is unavailable."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, indices=(0,), period_s=0.004):
+        self.indices, self.period = list(indices), period_s
+        self.sm, self.mx, self.reasons, self.stop_flag, self.thread, self.proc = [], [], set(), False, None, None
+
+    def _nvml_loop(self, nv, handles):
+        bits = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8)),
+                'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown',
+                                               getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40)),
+                'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown',
+                                               getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20)),
+                'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4))}
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        import time
+        while not self.stop_flag:
+            for h in handles:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(self.period)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            handles = [nv.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)) for h in handles]
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handles), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.rows = []
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -130,14 +164,20 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                    'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'nvml, %d GPU(s), every %.0f ms' % (len(self.indices), self.period * 1e3)}
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        rows = getattr(self, 'rows', [])
+        sm = [float(r[0]) for r in rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm), 'source': 'nvidia-smi -lms 100'}
 
 
 def oracle_cfg(w):
@@ -313,10 +353,11 @@ def main():
             first_loss = float(loss0)
     graphed = bool(getattr(trainer, '_graphs', None)) and all('graph' in g for g in trainer._graphs.values())
     ops.LAUNCH_COUNT = 0
-    clocks = ClockSampler(dev.index or 0)
-    clocks.start()
+    clocks = ClockSampler(range(world) if world > 1 else [dev.index or 0]) if rank == 0 else None      # ONE sampler for the whole job
+    if clocks is not None:
+        clocks.start()
     ms_total, loss = timed(args.steps, lambda i: resident[(args.warmup + i) % n_pool])
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks is not None else None
     final_loss = float(loss)
 
     # ---- eager pass 1 of the same steps: CUDA events around the HBM-roofline kernels only (few events: the pass stays GPU-bound) ----

@@ -99,11 +99,15 @@ __global__ void __launch_bounds__(KW * 32, MINB) score_partial_ring_kernel(const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
     // ---- ordered compaction of the owned entries (deterministic: chunk counts -> prefix -> scatter) ----
+    // the packed ids are staged in own_meta first: independent coalesced loads (one HBM latency for the whole row instead of one per
+    // 32-id chunk), then both passes run out of shared memory
     const int32_t* ids = p.ids + b * N;
     const int n32 = (N + 31) / 32;
+    for (int j = threadIdx.x; j < N; j += KW * 32) own_meta[j] = __ldg(ids + j);
+    __syncthreads();
     for (int c = warp; c < n32; c += KW) {
         const int j = c * 32 + lane;
-        const uint32_t pk = j < N ? (uint32_t)__ldg(ids + j) : 0u;
+        const uint32_t pk = j < N ? (uint32_t)own_meta[j] : 0u;
         const bool own = j < N && ((pk & kIdMask) % (uint32_t)p.W) == (uint32_t)p.r;
         const unsigned m = __ballot_sync(0xffffffffu, own);
         if (lane == 0) chunk_cnt[c + 1] = __popc(m);
@@ -115,16 +119,21 @@ __global__ void __launch_bounds__(KW * 32, MINB) score_partial_ring_kernel(const
         for (int c = 1; c <= n32; ++c) { tot += chunk_cnt[c]; chunk_cnt[c] = tot; }
     }
     __syncthreads();
-    for (int c = warp; c < n32; c += KW) {
-        const int j = c * 32 + lane;
-        const uint32_t pk = j < N ? (uint32_t)__ldg(ids + j) : 0u;
-        const uint32_t gid = pk & kIdMask;
-        const bool own = j < N && (gid % (uint32_t)p.W) == (uint32_t)p.r;
-        const unsigned m = __ballot_sync(0xffffffffu, own);
-        if (own) {
-            const int k = chunk_cnt[c] + __popc(m & ((1u << lane) - 1));
-            own_meta[k] = (int)((gid / (uint32_t)p.W) | (pk & 0x80000000u));
-            own_j[k] = (uint16_t)j;
+    // in-place scatter: entry k <= j always, chunks are processed in order by ONE warp so that no id is overwritten before it is read
+    if (warp == 0) {
+        for (int c = 0; c < n32; ++c) {
+            const int j = c * 32 + lane;
+            const uint32_t pk = j < N ? (uint32_t)own_meta[j] : 0u;
+            const uint32_t gid = pk & kIdMask;
+            const bool own = j < N && (gid % (uint32_t)p.W) == (uint32_t)p.r;
+            const unsigned m = __ballot_sync(0xffffffffu, own);
+            __syncwarp();
+            if (own) {
+                const int k = chunk_cnt[c] + __popc(m & ((1u << lane) - 1));
+                own_meta[k] = (int)((gid / (uint32_t)p.W) | (pk & 0x80000000u));
+                own_j[k] = (uint16_t)j;
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
