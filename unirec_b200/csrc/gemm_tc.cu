@@ -101,6 +101,7 @@ struct Params {
     int kb_per_split;       // k-blocks handled by one work unit along the split dimension
     int epi_bufs;           // store buffers per epilogue warp (1 or 2)
     int lo_stages;          // 3xTF32: depth of the lo ring
+    int split_warps;        // 3xTF32: number of operand-splitter warps (4 or 8)
     int dbg_skip;           // bring-up: bit0 skip TMA store issue, bit1 skip bias, bit2 skip smem staging
     int n_chunks, m_stripes, total_units, splits;
     const int* rows_dev; int rows_dim;   // optional device-resident token count: rows_dim 1 -> M = min(M, *rows_dev) (row-parallel GEMMs),
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
         if (p.preact) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
-        for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(ready + s, 4); }
+        for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(ready + s, kSplit ? p.split_warps : 1); }
         for (int s = 0; s < SL; ++s) mbar_init(lo_empty + s, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
     } else if (kSplit) {
         // ---------------- splitter: warps 10..13 ----------------
         const int tid = threadIdx.x - (2 + EPI_WARPS) * 32;
+        const int nsplit = p.split_warps * 32;
         const int n4 = (int)(raw_bytes >> 4);
         uint32_t it = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 float4* lo = reinterpret_cast<float4*>(lo_tiles + (size_t)sl * raw_bytes);
                 if (!(p.dbg_skip & 8))
 #pragma unroll 4
-                for (int i = tid; i < n4; i += 128) {
+                for (int i = tid; i < n4; i += nsplit) {
                     const float4 x = hi[i];
                     float4 h, l;
                     h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
@@ -581,6 +583,9 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     p.preact = preact; p.ldp = ldp; p.dact = dact; p.ldd = ldd; p.colsum = colsum;
     p.accumulate = accumulate ? (splits > 1 ? 1 : 2) : 0;
     p.kb_per_split = kb_per_split; p.epi_bufs = epi_bufs; p.lo_stages = lo_stages;
+    static const int env_sw = getenv("UR_TC_SPLIT_WARPS") ? atoi(getenv("UR_TC_SPLIT_WARPS")) : 0;
+    p.split_warps = 4;      // (8 splitter warps measured no faster: the split is not the limiter, profiles/r02/gemm_split_warps.txt)
+    (void)env_sw;
     static const int env_skip = getenv("UR_TC_SKIP") ? atoi(getenv("UR_TC_SKIP")) : 0;
     p.dbg_skip = env_skip;
     p.n_chunks = (int)(N / NC); p.m_stripes = (int)m_stripes; p.total_units = (int)(tiles * splits); p.splits = splits;
@@ -591,7 +596,7 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
 #define UR_TC_LAUNCH(AMN, BMN, SPL)                                                                                         \
     do {                                                                                                                    \
         cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-        gemm_tc_kernel<AMN, BMN, SPL><<<grid, SPL ? 448 : 320, smem, st>>>(tmA, tmB, tmC, tmP, p);                                    \
+        gemm_tc_kernel<AMN, BMN, SPL><<<grid, SPL ? (2 + EPI_WARPS + p.split_warps) * 32 : 320, smem, st>>>(tmA, tmB, tmC, tmP, p);                                    \
     } while (0)
     if (split3) {
         if (a_mn) UR_TC_LAUNCH(true, true, true);
