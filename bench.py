@@ -180,6 +180,52 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm), 'source': 'nvidia-smi -lms 100'}
 
 
+def nvlink_counters(index=0):
+    """(tx KiB, rx KiB) summed over the NVLink links of one GPU (`nvidia-smi nvlink -gt d`), or None when unsupported."""
+    try:
+        out = subprocess.run(['nvidia-smi', 'nvlink', '-gt', 'd', '-i', str(index)], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    tx = rx = 0
+    seen = False
+    for line in out.splitlines():
+        parts = line.replace(':', ' ').split()
+        if 'Tx' in parts or 'Rx' in parts:
+            try:
+                val = int(parts[parts.index('KiB') - 1])
+            except (ValueError, IndexError):
+                continue
+            seen = True
+            if 'Tx' in parts:
+                tx += val
+            else:
+                rx += val
+    return (tx, rx) if seen else None
+
+
+def nvlink_report(nv, w, B, K, L, d, W, live_frac):
+    """Measured NVLink bytes per step next to the algorithmic bytes the sharded step must move per rank (received):
+    packed ids, user vectors, partial softmax states / scores, (lse, n_y), history rows read from peers (forward + recompute in
+    the backward LayerNorm kernel) and their gradients pulled by the owners, encoder-gradient all-reduce."""
+    f = (W - 1.0) / W
+    S = W * B
+    algo = f * S * (1 + K) * 4 + f * S * d * 4
+    if w['loss_type'] == 'softmax':
+        algo += f * S * (4 + 2 * d) * 4 + f * S * 8
+    else:
+        algo += f * S * (1 + K) * 4 * 2 + f * S * d * 4
+    if w['model'] == 'SASRec':
+        algo += f * (S * L * 4 + 3 * B * L * live_frac * d * 4)
+    elif w['model'] == 'GRU':
+        algo += f * (S * L * 4 + 2 * S * L * d * 4)
+    elif w['model'] != 'MF':
+        algo += f * (S * L * 4 + 2 * S * d * 4)
+    out = dict(nv)
+    out['algorithmic_rx_bytes_per_step'] = algo
+    out['rx_over_algorithmic'] = nv['rx_bytes_per_step'] / algo if algo else None
+    return out
+
+
 def oracle_cfg(w):
     cfg = dict(COMMON)
     cfg.update({k: v for k, v in w.items() if k not in META_KEYS})
@@ -358,6 +404,15 @@ def main():
         clocks.start()
     ms_total, loss = timed(args.steps, lambda i: resident[(args.warmup + i) % n_pool])
     clk = clocks.stop() if clocks is not None else None
+    # NVLink traffic of the sharded step (N > 1): link counters of rank 0's GPU around an extra, untimed run of the same steps
+    nvlink = None
+    if world > 1:
+        c0 = nvlink_counters(dev.index or 0) if rank == 0 else None
+        timed(args.steps, lambda i: resident[(args.warmup + i) % n_pool])
+        c1 = nvlink_counters(dev.index or 0) if rank == 0 else None
+        if c0 is not None and c1 is not None:
+            nvlink = {'tx_bytes_per_step': (c1[0] - c0[0]) * 1024.0 / args.steps, 'rx_bytes_per_step': (c1[1] - c0[1]) * 1024.0 / args.steps,
+                      'source': 'nvidia-smi nvlink -gt d, GPU %d, all links, %d steps' % (dev.index or 0, args.steps)}
     final_loss = float(loss)
 
     # ---- eager pass 1 of the same steps: CUDA events around the HBM-roofline kernels only (few events: the pass stays GPU-bound) ----
@@ -542,6 +597,7 @@ def main():
                         'note': 'same steps launched eagerly (the pass the HBM roofline kernels are bracketed in)'},
         'roofline': roofline,
         'multi_gpu_loss_check': loss_check,
+        'nvlink': nvlink_report(nvlink, w, B, K, L, d, world, live_frac) if nvlink else None,
         'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
     }
     if not args.no_eager_baseline and world == 1:

@@ -574,6 +574,9 @@ template <int D4>
 static int launch_score_loss(const ScoreLossParams& p, int loss_type, size_t smem, cudaStream_t st) {
     const int spb = 8 / p.wps;
     const unsigned grid = (unsigned)((p.B + spb - 1) / spb);
+    // v2 ring kernel: the large-N path of the narrow rows (d <= 64); wide rows (d >= 128) take scoreloss_v3.cu, or the register-staged
+    // kernel below for the few shapes outside it -- the v2 kernel is not instantiated for them
+    if constexpr (D4 <= 16)
     if (p.wps == 8 && p.N >= 96 && g_use_bulk) {       // one sample per CTA, enough rows to fill the async ring
         const size_t bsm = score_loss_bulk_smem(D4 * 4, p.N);
         if (bsm <= 200 * 1024) {
