@@ -117,6 +117,101 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int M, int N, int K, con
     }
 }
 
+// Small-problem variant: 32 x 32 output tiles, 64 threads, 4 x 4 per thread.  The B-row GEMMs of the trimmed last encoder layer
+// (M = batch size, N, K in {128, 512}) give the 128 x 128-tile kernels (SIMT or tcgen05) only 4-32 CTAs and 13-30 us of pure latency
+// each; with 32 x 32 tiles the same products spread over 128-512 small CTAs.  Exact fp32 FMA, same epilogue options.
+constexpr int SBM = 32, SBN = 32, SBK = 8;
+
+template <bool KCONTIG>
+__device__ __forceinline__ float4 stile_load(const float* __restrict__ P, int64_t ld, int row0, int nrows, int k0, int kend, int t) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KCONTIG) {
+        const int r = row0 + (t >> 1), k = k0 + (t & 1) * 4;
+        if (r < nrows && k < kend) v = __ldg(reinterpret_cast<const float4*>(P + (int64_t)r * ld + k));
+    } else {
+        const int k = k0 + (t >> 3), r = row0 + (t & 7) * 4;
+        if (k < kend && r < nrows) v = __ldg(reinterpret_cast<const float4*>(P + (int64_t)k * ld + r));
+    }
+    return v;
+}
+template <bool KCONTIG>
+__device__ __forceinline__ void stile_store(float (*S)[SBM], const float4& v, int t) {
+    if (KCONTIG) {
+        const int r = t >> 1, k = (t & 1) * 4;
+        S[k + 0][r] = v.x; S[k + 1][r] = v.y; S[k + 2][r] = v.z; S[k + 3][r] = v.w;
+    } else {
+        const int k = t >> 3, r = (t & 7) * 4;
+        *reinterpret_cast<float4*>(&S[k][r]) = v;
+    }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(64) gemm_simt_small_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
+                                                             const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
+                                                             const float* __restrict__ bias, int act, float* __restrict__ preact,
+                                                             int64_t ldp, int accumulate, int k_chunk) {
+    __shared__ __align__(16) float As[2][SBK][SBM];
+    __shared__ __align__(16) float Bs[2][SBK][SBN];
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+    const int kbeg = blockIdx.z * k_chunk;
+    const int kend = min(K, kbeg + k_chunk);
+    const int tx = t & 7, ty = t >> 3;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float4 ra = stile_load<!TA>(A, lda, m0, M, kbeg, kend, t);
+    float4 rb = stile_load<TB>(B, ldb, n0, N, kbeg, kend, t);
+    stile_store<!TA>(As[0], ra, t);
+    stile_store<TB>(Bs[0], rb, t);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += SBK) {
+        const bool more = k0 + SBK < kend;
+        if (more) {
+            ra = stile_load<!TA>(A, lda, m0, M, k0 + SBK, kend, t);
+            rb = stile_load<TB>(B, ldb, n0, N, k0 + SBK, kend, t);
+        }
+#pragma unroll
+        for (int kk = 0; kk < SBK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) {
+            stile_store<!TA>(As[buf ^ 1], ra, t);
+            stile_store<TB>(Bs[buf ^ 1], rb, t);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    const bool lead = blockIdx.z == 0;
+    const int n = n0 + tx * 4;
+    if (n >= N) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (bias && lead) v = f4_add(v, __ldg(reinterpret_cast<const float4*>(bias + n)));
+        if (preact) *reinterpret_cast<float4*>(preact + (int64_t)m * ldp + n) = v;
+        if (act != ACT_NONE) {
+            v.x = act_fwd(v.x, act); v.y = act_fwd(v.y, act); v.z = act_fwd(v.z, act); v.w = act_fwd(v.w, act);
+        }
+        float* c = C + (int64_t)m * ldc + n;
+        if (accumulate == 1) red_add_v4(c, v);
+        else if (accumulate == 2) *reinterpret_cast<float4*>(c) = f4_add(*reinterpret_cast<float4*>(c), v);
+        else *reinterpret_cast<float4*>(c) = v;
+    }
+}
+
 // dX *= act'(preact)   (backward of the fused activation epilogue)
 __global__ void __launch_bounds__(256) act_bwd_kernel(float4* __restrict__ dY, const float4* __restrict__ pre, int64_t n4, int act) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -160,6 +255,33 @@ static int gemm_simt_launch(int transA, int transB, int64_t M, int64_t N, int64_
     if (transB && (K & 3)) return UR_ERR_BAD_ARG;       // B contiguous along k
     if (preact && (ldp & 3)) return UR_ERR_BAD_ARG;
     if (M == 0 || N == 0) return UR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // small problems (at most 32 tiles of 128 x 128, no device-side row bound): 32 x 32 tiles over many small CTAs
+    if (!rows_dev && ((M + ur::BM - 1) / ur::BM) * ((N + ur::BN - 1) / ur::BN) <= 32 && K <= 4096) {
+        const int sgx = (int)((N + ur::SBN - 1) / ur::SBN), sgy = (int)((M + ur::SBM - 1) / ur::SBM);
+        int ssplits = 1;
+        int64_t sk_chunk = K;
+        if (accumulate && !preact && act == 0) {
+            const int64_t tiles = (int64_t)sgx * sgy;
+            const int64_t want = (2 * ur::kNumSMs + tiles - 1) / tiles;
+            const int64_t maxs = (K + 127) / 128;
+            ssplits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
+            sk_chunk = ((K + ssplits - 1) / ssplits + ur::SBK - 1) / ur::SBK * ur::SBK;
+            ssplits = (int)((K + sk_chunk - 1) / sk_chunk);
+            if (ssplits < 1) { ssplits = 1; sk_chunk = K; }
+        }
+        const int sacc = accumulate ? (ssplits > 1 ? 1 : 2) : 0;
+        dim3 sgrid(sgx, sgy, ssplits);
+#define UR_SGEMM(TA, TB)                                                                                                     \
+    ur::gemm_simt_small_kernel<TA, TB><<<sgrid, 64, 0, st>>>((int)M, (int)N, (int)K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, \
+                                                             sacc, (int)sk_chunk)
+        if (!transA && !transB) UR_SGEMM(false, false);
+        else if (!transA && transB) UR_SGEMM(false, true);
+        else if (transA && !transB) UR_SGEMM(true, false);
+        else UR_SGEMM(true, true);
+#undef UR_SGEMM
+        UR_RETURN_LAST_ERROR();
+    }
     const int gx = (int)((N + ur::BN - 1) / ur::BN), gy = (int)((M + ur::BM - 1) / ur::BM);
     int splits = 1;
     int64_t k_chunk = K;
@@ -175,7 +297,6 @@ static int gemm_simt_launch(int transA, int transB, int64_t M, int64_t N, int64_
     }
     if (accumulate) accumulate = splits > 1 ? 1 : 2;    // atomics only when several CTAs share an output tile
     dim3 grid(gx, gy, splits);
-    cudaStream_t st = (cudaStream_t)stream;
 #define UR_GEMM(TA, TB)                                                                                                   \
     ur::gemm_simt_kernel<TA, TB><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, A, lda, B, ldb, C, ldc, bias, act, preact, ldp, \
                                                        accumulate, (int)k_chunk, rows_dev, rows_dim)
