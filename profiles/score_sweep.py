@@ -15,7 +15,7 @@ for N in (1025,):
     scores, dscore = torch.empty(B, N, device='cuda'), torch.empty(B, N, device='cuda')
     lv, gu, npos = torch.empty(B, device='cuda'), torch.empty(B, d, device='cuda'), torch.full((1,), float(B), device='cuda')
     ref = None
-    for mode, name in ((0, 'register-staged v1'), (2, 'bulk ring v2'), (10, 'v3 2 lanes/row, 4 warps'), (11, 'v3 4 lanes/row, 8 warps'), (12, 'v3 2l 3w 4st'), (13, 'v3 2l 6w 2st'), (14, 'v3 4l 2w 2st x7'), (15, 'v3 2l 1w 2st x7'), (16, 'v3 4l 2w 2st x4'), (17, 'v3 2l 2w 2st x5')):
+    for mode, name in ((0, 'register-staged v1'), (2, 'bulk ring v2'), (10, 'v3 2 lanes/row, 4 warps'), (11, 'v3 4 lanes/row, 8 warps'), (12, 'v3 2l 3w 4st'), (13, 'v3 2l 6w 2st'), (14, 'v3 4l 2w 2st x7'), (15, 'v3 2l 1w 2st x7'), (16, 'v3 4l 2w 2st x4'), (17, 'v3 2l 2w 2st x5'), (18, 'v3 2l 12w 2st x1'), (19, 'v3 2l 8w 3st x1'), (26, 'v3 2l 10w 2st x1'), (27, 'v3 2l 8w 2st x1')):
         lib.ur_score_loss_set_bulk(mode)
         def run(i):
             ops.score_loss(table, u, ids[i % 8], 'softmax', label=lab, norm_dev=npos, scores=scores, loss_vec=lv, dscore=dscore, grad_user=gu)

@@ -360,8 +360,23 @@ int score_loss_v3_try(const ScoreLossParams& p, int d, int loss_type, cudaStream
             if (var == 5) { const int rc = v3::launch<128, 2, 1, 2, 7>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
             if (var == 6) { const int rc = v3::launch<128, 4, 2, 2, 4>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
             if (var == 7) { const int rc = v3::launch<128, 2, 2, 2, 5>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            // one big CTA per SM (round 2: the d = 256 sweep favoured 8 warps x 1 CTA over 6 warps x 2 CTAs)
+            if (var == 8) { const int rc = v3::launch<128, 2, 12, 2, 1>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 9) { const int rc = v3::launch<128, 2, 8, 3, 1>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 16) { const int rc = v3::launch<128, 2, 10, 2, 1>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 17) { const int rc = v3::launch<128, 2, 8, 2, 1>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
             return v3::launch<128, 2, 6, 2>(p, loss_type, st);
-        case 256: return v3::launch<256, 4, 6, 2>(p, loss_type, st);
+        case 256:          // tuning switch for the wide row (profiles/score_sweep.py D=256)
+            if (var == 10) { const int rc = v3::launch<256, 4, 6, 3, 1>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 11) { const int rc = v3::launch<256, 4, 4, 3, 2>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 12) { const int rc = v3::launch<256, 4, 3, 4, 2>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 13) { const int rc = v3::launch<256, 8, 6, 2, 2>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 14) { const int rc = v3::launch<256, 4, 8, 2, 1>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            if (var == 15) { const int rc = v3::launch<256, 4, 4, 2, 3>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            // default (measured, profiles/r02/score_sweep_d256.txt, N = 4097): 8 warps x 2-deep ring, ONE CTA per SM = 88% of the HBM copy peak
+            // (6 warps x 2 CTAs/SM does not fit next to a 4097-entry score buffer and fell back to the register-staged kernel: 39%)
+            { const int rc = v3::launch<256, 4, 8, 2, 1>(p, loss_type, st); if (rc != UR_ERR_UNSUPPORTED) return rc; }
+            return v3::launch<256, 4, 6, 2>(p, loss_type, st);
         case 512: return v3::launch<512, 8, 6, 2>(p, loss_type, st);
         default: return UR_ERR_UNSUPPORTED;
     }

@@ -13,6 +13,7 @@
 // BPR under sharding (three small phases, K is small there): ur_shard_scores_f32 (owned raw scores), ur_bpr_from_scores_f32 (home: loss,
 // dLoss/ds), ur_shard_grad_user_f32 (owner: partial dLoss/du).
 // Arithmetic = scoreloss.cu / scoreloss_v3.cu (reference: unirec/model/base/recommender.py:76-96, reco_abc.py:252-265, modules.py:15-21).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ur {
@@ -517,12 +518,27 @@ int ur_score_partial_f32(const float* table_local, int d, const float* user_emb,
     p.N = N; p.W = world; p.r = rank; p.S = S; p.z = z; p.state = state;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = UR_ERR_UNSUPPORTED;
+    static const int variant = getenv("UR_PARTIAL_VARIANT") ? atoi(getenv("UR_PARTIAL_VARIANT")) : 0;     // profiles/scripts/partial_sweep.py
     if (N >= 64) {
-        // ~N/W owned rows per sample: two warps with a 2-deep ring each, 5 (d=128) / 3 (d=256) CTAs per SM
-        if (d == 128) rc = ur::sr::launch_ring<128, 2, 2, 2, 5>(p, st);
-        else if (d == 256) rc = ur::sr::launch_ring<256, 4, 2, 2, 3>(p, st);
-        if (rc == UR_ERR_UNSUPPORTED && d == 128) rc = ur::sr::launch_ring<128, 2, 2, 2, 2>(p, st);
-        if (rc == UR_ERR_UNSUPPORTED && d == 256) rc = ur::sr::launch_ring<256, 4, 2, 2, 1>(p, st);
+        // ~N/W owned rows per sample: few warps with a 2-deep ring each, several CTAs per SM
+        if (d == 128) {
+            // measured at W = 8, N = 1025, S = 8192 (profiles/r02/partial_sweep.txt): one warp per sample, 8 CTAs per SM = 0.179 ms;
+            // 2 warps x 5 CTAs 0.219 ms; 4 warps x 2 CTAs 0.261 ms
+            if (variant == 1) rc = ur::sr::launch_ring<128, 2, 4, 2, 2>(p, st);
+            else if (variant == 3) rc = ur::sr::launch_ring<128, 2, 2, 3, 4>(p, st);
+            else if (variant == 4) rc = ur::sr::launch_ring<128, 2, 1, 3, 7>(p, st);
+            else if (variant == 5) rc = ur::sr::launch_ring<128, 2, 2, 2, 5>(p, st);
+            if (rc == UR_ERR_UNSUPPORTED) rc = ur::sr::launch_ring<128, 2, 1, 2, 8>(p, st);
+            if (rc == UR_ERR_UNSUPPORTED) rc = ur::sr::launch_ring<128, 2, 2, 2, 5>(p, st);
+            if (rc == UR_ERR_UNSUPPORTED) rc = ur::sr::launch_ring<128, 2, 2, 2, 2>(p, st);
+        } else if (d == 256) {
+            if (variant == 1) rc = ur::sr::launch_ring<256, 4, 4, 2, 2>(p, st);
+            else if (variant == 2) rc = ur::sr::launch_ring<256, 4, 1, 2, 6>(p, st);
+            else if (variant == 3) rc = ur::sr::launch_ring<256, 4, 8, 2, 1>(p, st);
+            else if (variant == 4) rc = ur::sr::launch_ring<256, 4, 2, 3, 2>(p, st);
+            if (rc == UR_ERR_UNSUPPORTED) rc = ur::sr::launch_ring<256, 4, 2, 2, 3>(p, st);
+            if (rc == UR_ERR_UNSUPPORTED) rc = ur::sr::launch_ring<256, 4, 2, 2, 1>(p, st);
+        }
     }
     if (rc == UR_ERR_UNSUPPORTED) {
         ur::sr::score_partial_simple_kernel<<<(unsigned)((S + 7) / 8), 256, 0, st>>>(p, d / 4);
