@@ -34,6 +34,10 @@ int ur_has_tensor_core_gemm(void);
 int ur_gather_rows_f32(const float* table, int64_t n_rows, int d, const void* idx, int idx_bits /*32|64*/, int64_t n,
                        float* out, void* stream);
 
+/* BF16 table copy (opt-in reduced-precision mode, north_star 1e-2 bar): out[i,:] = float(table_bf16[idx[i],:]), d % 8 == 0 */
+int ur_gather_rows_bf16(const void* table_bf16, int64_t n_rows, int d, const void* idx, int idx_bits /*32|64*/, int64_t n, float* out,
+                        void* stream);
+
 /* ---- K11 (exact-dense mode): grad[idx[i],:] += coef * src[i / src_group,:], rows with idx == pad_id skipped.
  * replaces: embedding_dense_backward under accelerator.backward, unirec/facility/trainer.py:346 */
 int ur_scatter_add_rows_f32(float* grad, int64_t n_rows, int d, const void* idx, int idx_bits, int64_t n, const float* src,

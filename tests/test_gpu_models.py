@@ -404,3 +404,16 @@ def test_gru_persistent_recurrence_matches_reference(name):
         ref = g.grads[k]
         err = float((p.grad.cpu().double() - ref.double()).abs().max())
         assert err <= TOL * max(float(ref.abs().max()), 1e-2 * scale), (k, err)
+
+
+def test_reference_checkpoint_scores_on_the_cuda_path():
+    """The reference-written checkpoint (tests/golden_eval/reference_checkpoint_mf.pth) evaluated by the CUDA path reproduces the scores
+    the reference model computed before saving."""
+    import os
+    from unirec_b200.utils import general
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden_eval', 'reference_checkpoint_mf.pth')
+    model, _ = general.load_model_freely(path, device=torch.device(DEV))
+    probe = torch.load(path, map_location='cpu', weights_only=False)['_probe']
+    model.eval()
+    _, scores, _, _ = model(user_id=probe['user_id'].to(DEV), item_id=probe['item_id'].to(DEV))
+    assert rel_err(scores.cpu(), probe['scores']) < TOL

@@ -542,3 +542,13 @@ def test_persistent_gru_recurrence_matches_stepwise_path(H, B, L):
     # dW_hh = sum_t dgh[t]^T h_{t-1} (formed by the GEMM in the engine): check the dgh the kernel emits through it
     dw = torch.einsum('tbj,tbk->jk', dgh.double(), hs[:-1].double())
     assert float((dw - w64.grad).abs().max()) < 5e-5 * max(1.0, float(w64.grad.abs().max()))
+
+
+def test_gather_rows_bf16_is_exact_widening():
+    from unirec_b200 import ops
+    torch.manual_seed(2)
+    table = (torch.randn(5000, 128, device=DEV) * 0.3).to(torch.bfloat16)
+    for dt in (torch.int32, torch.int64):
+        idx = torch.randint(0, 5000, (37, 11), device=DEV).to(dt)
+        out = ops.gather_rows_bf16(table, idx)
+        assert torch.equal(out, table[idx.long()].float())

@@ -141,3 +141,17 @@ def test_install_as_unirec_alias_resolves_reference_imports():
             "assert callable(main.run); print('ALIAS_OK')" % root)
     res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120, cwd='/tmp')
     assert res.returncode == 0 and 'ALIAS_OK' in res.stdout, res.stdout + res.stderr
+
+
+def test_reference_written_checkpoint_loads_into_drop_in_classes():
+    """§8 f4: a checkpoint written by the reference (its model class, its dict layout: trainer.py:389-398; fixture from
+    oracle/make_ckpt_golden.py) is rebuilt by load_model_freely into the unirec_b200 class with identical weights."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden_eval', 'reference_checkpoint_mf.pth')
+    cpt = torch.load(path, map_location='cpu', weights_only=False)
+    assert {'config', 'cur_epoch', 'cur_step', 'best_valid_score', 'state_dict', 'optimizer', 'scheduler'} <= set(cpt)
+    model, cfg = general.load_model_freely(path, device=torch.device('cpu'))
+    assert type(model).__module__.startswith('unirec_b200.') and type(model).__name__ == 'MF'
+    sd = model.state_dict()
+    assert set(sd) == set(cpt['state_dict'])
+    for k, v in cpt['state_dict'].items():
+        assert torch.equal(sd[k], v), k

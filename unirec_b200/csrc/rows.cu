@@ -35,6 +35,26 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restri
     }
 }
 
+// out[i, :] = float(table_bf16[idx[i], :]): gather from a BF16 copy of a table (half the HBM bytes per row; north_star's opt-in
+// 1e-2 mode).  One thread moves 8 elements: one 16-byte load -> two float4 stores.  Exact widening (bf16 -> fp32 is a shift).
+__global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const uint4* __restrict__ table, const void* __restrict__ idx, int idx64,
+                                                               int64_t n, int d8, float4* __restrict__ out) {
+    const int64_t total = n * d8;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d8;
+        const int c = (int)(e - r * d8);
+        const int64_t id = load_index(idx, idx64, r);
+        const uint4 v = __ldg(table + id * d8 + c);
+        float4 lo, hi;
+        lo.x = __uint_as_float(v.x << 16); lo.y = __uint_as_float(v.x & 0xffff0000u);
+        lo.z = __uint_as_float(v.y << 16); lo.w = __uint_as_float(v.y & 0xffff0000u);
+        hi.x = __uint_as_float(v.z << 16); hi.y = __uint_as_float(v.z & 0xffff0000u);
+        hi.z = __uint_as_float(v.w << 16); hi.w = __uint_as_float(v.w & 0xffff0000u);
+        out[e * 2] = lo;
+        out[e * 2 + 1] = hi;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // grad[idx[i], :] += src[i, :] * (coef ? coef[i / group] : 1), rows with idx == pad_id skipped.
 // Exact-dense mode of K11 (what embedding_dense_backward produces), one RED.v4 per 16 bytes.
@@ -158,6 +178,18 @@ int ur_scatter_add_rows_f32(float* grad, int64_t n_rows, int d, const void* idx,
     if (blocks > cap) blocks = cap;
     ur::scatter_add_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         grad, idx, idx_bits == 64, n, d4, reinterpret_cast<const float4*>(src), src_group, coef, coef_group, pad_id);
+    UR_RETURN_LAST_ERROR();
+}
+
+int ur_gather_rows_bf16(const void* table_bf16, int64_t n_rows, int d, const void* idx, int idx_bits, int64_t n, float* out, void* stream) {
+    if (d <= 0 || (d & 7) || (idx_bits != 32 && idx_bits != 64)) return UR_ERR_BAD_ARG;
+    if (n == 0) return UR_OK;
+    (void)n_rows;
+    int64_t blocks = (n * (d / 8) + 255) / 256;
+    const int64_t cap = (int64_t)ur::kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    ur::gather_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)table_bf16, idx, idx_bits == 64, n, d / 8,
+                                                                                    (float4*)out);
     UR_RETURN_LAST_ERROR();
 }
 

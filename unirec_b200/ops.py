@@ -87,6 +87,16 @@ def gather_rows(table, idx, out=None):
     return out
 
 
+def gather_rows_bf16(table_bf16, idx, out=None):
+    """Gather from a BF16 copy of a table, widened to fp32 (exact)."""
+    assert table_bf16.dtype == torch.bfloat16 and table_bf16.is_contiguous() and idx.is_contiguous()
+    d = table_bf16.shape[1]
+    if out is None:
+        out = torch.empty(*idx.shape, d, dtype=torch.float32, device=table_bf16.device)
+    _call('ur_gather_rows_bf16', _ptr(table_bf16), table_bf16.shape[0], d, _ptr(idx), _idx_bits(idx), idx.numel(), _f32(out), _stream())
+    return out
+
+
 def scatter_add_rows(grad, idx, src, src_group=1, coef=None, coef_group=1, pad_id=0):
     assert grad.is_contiguous() and idx.is_contiguous() and src.is_contiguous()
     _call('ur_scatter_add_rows_f32', _f32(grad), grad.shape[0], grad.shape[1], _ptr(idx), _idx_bits(idx), idx.numel(),
