@@ -34,6 +34,11 @@ int ur_has_tensor_core_gemm(void);
 int ur_gather_rows_f32(const float* table, int64_t n_rows, int d, const void* idx, int idx_bits /*32|64*/, int64_t n,
                        float* out, void* stream);
 
+/* scalar tables: out[idx[e / idx_group] & idx_mask] += src[e], e < n.  replaces: autograd of `+ user_bias[user_id] + item_bias[item_id]`,
+ * unirec/model/base/recommender.py:79-90 (idx_group 1: item bias, one id per entry; idx_group N: user bias, one id per sample) */
+int ur_scatter_add_scalar_f32(float* out, const void* idx, int idx_bits, int64_t idx_group, int64_t idx_mask, const float* src, int64_t n,
+                              void* stream);
+
 /* BF16 table copy (opt-in reduced-precision mode, north_star 1e-2 bar): out[i,:] = float(table_bf16[idx[i],:]), d % 8 == 0 */
 int ur_gather_rows_bf16(const void* table_bf16, int64_t n_rows, int d, const void* idx, int idx_bits /*32|64*/, int64_t n, float* out,
                         void* stream);

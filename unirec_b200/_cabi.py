@@ -16,6 +16,7 @@ SIGNATURES = {
     'ur_version': '',
     'ur_has_tensor_core_gemm': '',
     'ur_gather_rows_f32': 'plipilpp',
+    'ur_scatter_add_scalar_f32': 'ppillplp',
     'ur_gather_rows_bf16': 'plipilpp',
     'ur_scatter_add_rows_f32': 'plipilplpllp',
     'ur_pool_sum_fwd_f32': 'piplipfpppp' + 'ii' + 'p',

@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(float* __restrict
     }
 }
 
+// out[idx[e / idx_group] & mask] += src[e] for e < n  (scalar tables: item_bias / user_bias gradients, recommender.py:79-90).
+// idx_group = 1: one index per entry (item bias); idx_group = N: one index per sample, its N entries summed (user bias).
+__global__ void __launch_bounds__(256) scatter_add_scalar_kernel(float* __restrict__ out, const void* __restrict__ idx, int idx64,
+                                                                 int64_t idx_group, int64_t mask, const float* __restrict__ src, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float v = src[e];
+        if (v != 0.f) atomicAdd(out + (load_index(idx, idx64, e / idx_group) & mask), v);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sum-pool tower (AvgHist / SVD++ / MF user side):
 //   u[b,:] = (U ? U[user_id[b],:] : 0) + coeff[b] * sum_l E[seq[b,l],:],  coeff[b] = (len[b]+1)^-alpha
@@ -178,6 +188,17 @@ int ur_scatter_add_rows_f32(float* grad, int64_t n_rows, int d, const void* idx,
     if (blocks > cap) blocks = cap;
     ur::scatter_add_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         grad, idx, idx_bits == 64, n, d4, reinterpret_cast<const float4*>(src), src_group, coef, coef_group, pad_id);
+    UR_RETURN_LAST_ERROR();
+}
+
+int ur_scatter_add_scalar_f32(float* out, const void* idx, int idx_bits, int64_t idx_group, int64_t idx_mask, const float* src, int64_t n,
+                              void* stream) {
+    if ((idx_bits != 32 && idx_bits != 64) || idx_group < 1) return UR_ERR_BAD_ARG;
+    if (n == 0) return UR_OK;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ur::kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    ur::scatter_add_scalar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, idx, idx_bits == 64, idx_group, idx_mask, src, n);
     UR_RETURN_LAST_ERROR();
 }
 

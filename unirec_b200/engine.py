@@ -821,10 +821,9 @@ class Engine:
             dscore = dscore * grad_out
         fp = self.flat
         if m.has_item_bias:
-            gb = fp.g('item_bias')
-            gb.index_add_(0, st['item_id'].reshape(-1), dscore.reshape(-1))
+            ops.scatter_add_scalar(fp.g('item_bias'), st['item_id'], dscore.contiguous())
         if m.has_user_bias:
-            fp.g('user_bias').index_add_(0, st['user_id'], dscore.sum(1))
+            ops.scatter_add_scalar(fp.g('user_bias'), st['user_id'].contiguous(), dscore.contiguous(), idx_group=st['N'])
         self.rowgrad(self.table_for_target()).add(st['item_id'], st['user'], st['N'], dscore, 1)
         self.tower.backward(d_user)
 

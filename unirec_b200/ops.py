@@ -87,6 +87,14 @@ def gather_rows(table, idx, out=None):
     return out
 
 
+def scatter_add_scalar(out, idx, src, idx_group=1, idx_mask=-1):
+    """out[idx[e // idx_group] & idx_mask] += src.flat[e] (bias-vector gradients)."""
+    assert out.is_contiguous() and idx.is_contiguous() and src.is_contiguous()
+    _call('ur_scatter_add_scalar_f32', _f32(out), _ptr(idx), _idx_bits(idx), int(idx_group), int(idx_mask), _f32(src), src.numel(),
+          _stream())
+    return out
+
+
 def gather_rows_bf16(table_bf16, idx, out=None):
     """Gather from a BF16 copy of a table, widened to fp32 (exact)."""
     assert table_bf16.dtype == torch.bfloat16 and table_bf16.is_contiguous() and idx.is_contiguous()

@@ -413,10 +413,9 @@ class ShardedEngine(Engine):
         # bias gradients (replicated [V] / [n_users] vectors in the flat buffer): every rank adds the entries it owns (dscore is zero
         # elsewhere), the all-reduce of the flat gradient buffer completes the sum
         if m.has_item_bias:
-            idx = (st['ids_all'].reshape(-1) & ops.PACKED_ID_MASK).long()
-            self.flat.g('item_bias').index_add_(0, idx, dscore.reshape(-1))
+            ops.scatter_add_scalar(self.flat.g('item_bias'), st['ids_all'], dscore.contiguous(), idx_mask=ops.PACKED_ID_MASK)
         if m.has_user_bias:
-            self.flat.g('user_bias').index_add_(0, st['uid_all'], dscore.sum(1))
+            ops.scatter_add_scalar(self.flat.g('user_bias'), st['uid_all'], dscore.contiguous(), idx_group=st['N'])
         self.rowgrad(self.table_for_target()).add(st['keys'], st['user'], st['N'], dscore, 1, key_mask=ops.PACKED_ID_MASK)
         self.tower.backward(d_user)
 
