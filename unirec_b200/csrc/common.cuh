@@ -56,6 +56,29 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// L2 evict-first policy for data that is touched once per step (table rows, Adam moments): streaming it with normal priority pushes
+// the step's activations out of the 126 MB L2 and turns their dirty lines into HBM write-backs in the middle of the streaming kernel
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld_stream_rw_ef(const float4* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg_stream_ef(float4* p, const float4& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ldg_stream_ef(const float4* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
 // vector reduction into global memory (no return value): one 16-byte RED per lane
 __device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"

@@ -10,6 +10,7 @@
 // The softmax branch is a single-query attention: an online (max, sum, weighted-row-sum) recurrence gives
 // dL/du = (n_b * sum_j p_j m_j e_j - sum_j y_j m_j e_j) / (P tau) without a second pass over the rows
 // (m_j = clamp pass-through mask, n_b = positives in row b, P = positives in the batch).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ur {
@@ -32,6 +33,7 @@ struct ScoreLossParams {
     float* loss_vec;          // [B]
     float* dscore;            // [B, N] dLoss/d(dot)   (may be null -> forward only)
     float4* grad_user;        // [B, d]                (may be null -> forward only)
+    int l2_evict_first;       // v3 kernel: stream the rows through L2 with evict-first priority (must match scoreloss_v3.cu)
 };
 
 constexpr float kBprEps = 1e-8f;   // unirec/constants/global_variables.py:4
@@ -639,6 +641,8 @@ int ur_score_loss_fwd_bwd_f32(const float* table, int d, const float* user_emb, 
     p.item_bias = item_bias; p.user_bias = user_bias; p.user_id = user_id; p.norm_dev = norm_dev; p.norm_host = norm_host;
     p.inv_tau = 1.f / tau; p.clip = score_clip; p.N = N; p.B = B;
     p.scores = scores; p.loss_vec = loss_vec; p.dscore = dscore; p.grad_user = (float4*)grad_user;
+    static const int env_evict = getenv("UR_SCORE_EVICT_FIRST") ? atoi(getenv("UR_SCORE_EVICT_FIRST")) : 1;
+    p.l2_evict_first = env_evict;
     const int rpw = d >= 128 ? 1 : 128 / d;
     int wps = 1;
     while (wps < 8 && N > wps * rpw * 8) wps *= 2;     // >= 8 rows per group before adding warps

@@ -19,6 +19,7 @@ struct ScoreLossParams {     // must match scoreloss.cu
     const float* item_bias; const float* user_bias; const int64_t* user_id; const float* norm_dev;
     float norm_host; float inv_tau, clip; int N; int64_t B; int wps;
     float* scores; float* loss_vec; float* dscore; float4* grad_user;
+    int l2_evict_first;
 };
 
 namespace v3 {
@@ -74,6 +75,10 @@ __global__ void __launch_bounds__(KW * 32, MINB) score_loss_v3_kernel(const Scor
     const bool has_clip = clip > 0.f;
     const float ub = p.user_bias ? __ldg(p.user_bias + __ldg(p.user_id + b)) : 0.f;
     const int r_dot = lane / LR, h_dot = lane % LR;
+    // The table rows are read exactly once per step: stream them through L2 with evict-first priority, so that they do not push out
+    // the encoder activations the backward pass is about to re-read (whose dirty lines would be written back during this kernel).
+    uint64_t l2_policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_policy));
 
     // u: the 16 float4 this lane needs in the dot phase (interleaved parts: float4 index k*LR + h)
     float4 ureg[UPL];
@@ -130,8 +135,12 @@ __global__ void __launch_bounds__(KW * 32, MINB) score_loss_v3_kernel(const Scor
         sid[slot] = nid; slab[slot] = nlab;
         if (lane < nvalid) {
             const uint32_t dst = smem_u32(ring + (size_t)(slot * RPC + lane) * ROWP);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(reinterpret_cast<const float*>(p.table) + nid * D), "r"((uint32_t)ROWB), "r"(bar) : "memory");
+            if (p.l2_evict_first)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(dst), "l"(reinterpret_cast<const float*>(p.table) + nid * D), "r"((uint32_t)ROWB), "r"(bar), "l"(l2_policy) : "memory");
+            else
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(reinterpret_cast<const float*>(p.table) + nid * D), "r"((uint32_t)ROWB), "r"(bar) : "memory");
         }
     };
 

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(KW * 32, MINB) score_partial_ring_kernel(const
     const bool has_clip = clip > 0.f;
     const float ub = p.user_bias ? __ldg(p.user_bias + __ldg(p.user_id + b)) : 0.f;
     const int r_dot = lane / LR, h_dot = lane % LR;
+    const uint64_t l2_policy = l2_evict_first_policy();      // rows are read once per step (see scoreloss_v3.cu)
     float4 ureg[UPL];
 #pragma unroll
     for (int i = 0; i < UPL; ++i) ureg[i] = __ldg(p.user_emb + b * D4 + i * LR + h_dot);
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(KW * 32, MINB) score_partial_ring_kernel(const
         if (lane < nvalid) {
             const uint32_t dst = smem_u32(ring + (size_t)(slot * RPC + lane) * ROWP);
             const int64_t lrow = (int64_t)(meta & 0x7FFFFFFF);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(reinterpret_cast<const float*>(p.table) + lrow * D), "r"((uint32_t)ROWB), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(dst), "l"(reinterpret_cast<const float*>(p.table) + lrow * D), "r"((uint32_t)ROWB), "r"(bar), "l"(l2_policy) : "memory");
         }
     };
 #pragma unroll

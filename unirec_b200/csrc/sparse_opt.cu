@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
     const int nu = u_end_dev ? *u_end_dev : *n_uniq;
     const bool skip = h.skip_flag && *h.skip_flag != 0;
     const float gs = h.grad_scale_dev ? *h.grad_scale_dev : 1.f;
+    const uint64_t pol = l2_evict_first_policy();        // parameter / moment rows are touched once per step: stream them through L2
     float bc1 = 1.f, bc2s = 1.f;
     if (mode == OPT_ADAM || mode == OPT_ADAMW) {
         const float t = (float)(*h.step_dev);
@@ -117,8 +118,8 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const int64_t o = id * D4 + v * LPR + col;
-                P[v] = ld_stream_rw(table + o);
-                if (is_adam) { M[v] = ld_stream_rw(mom + o); W[v] = ld_stream_rw(var + o); }
+                P[v] = ld_stream_rw_ef(table + o, pol);
+                if (is_adam) { M[v] = ld_stream_rw_ef(mom + o, pol); W[v] = ld_stream_rw_ef(var + o, pol); }
             }
         }
         const int32_t e_next = id_next >= 0 ? head[id_next] : -1;       // distinct row: not the head reset below
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
             float4 gg = f4_scale(g[v], gs);
             if (mode == OPT_SGD) {
                 if (h.weight_decay != 0.f) gg = f4_fma(h.weight_decay, p, gg);
-                stg_stream(table + o, f4_fma(-h.lr, gg, p));
+                stg_stream_ef(table + o, f4_fma(-h.lr, gg, p), pol);
             } else {
                 if (mode == OPT_ADAM && h.weight_decay != 0.f) gg = f4_fma(h.weight_decay, p, gg);
                 if (mode == OPT_ADAMW && h.weight_decay != 0.f) p = f4_scale(p, 1.f - h.lr * h.weight_decay);
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) rowlist_apply_kernel(float4* table, float
                 const float a = h.lr / bc1;
                 p.x -= a * m.x / (sqrtf(w.x) / bc2s + h.eps); p.y -= a * m.y / (sqrtf(w.y) / bc2s + h.eps);
                 p.z -= a * m.z / (sqrtf(w.z) / bc2s + h.eps); p.w -= a * m.w / (sqrtf(w.w) / bc2s + h.eps);
-                stg_stream(mom + o, m); stg_stream(var + o, w); stg_stream(table + o, p);
+                stg_stream_ef(mom + o, m, pol); stg_stream_ef(var + o, w, pol); stg_stream_ef(table + o, p, pol);
             }
         }
         id = id_next; e = e_next;
