@@ -257,7 +257,7 @@ static int gemm_simt_launch(int transA, int transB, int64_t M, int64_t N, int64_
     if (M == 0 || N == 0) return UR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     // small problems (at most 32 tiles of 128 x 128, no device-side row bound): 32 x 32 tiles over many small CTAs
-    if (!rows_dev && ((M + ur::BM - 1) / ur::BM) * ((N + ur::BN - 1) / ur::BN) <= 32 && K <= 4096) {
+    if (!rows_dev && ((M + ur::BM - 1) / ur::BM) * ((N + ur::BN - 1) / ur::BN) <= 32 && K <= 4096 && M * N * K <= (int64_t)80 * 1000 * 1000) {
         const int sgx = (int)((N + ur::SBN - 1) / ur::SBN), sgy = (int)((M + ur::SBM - 1) / ur::SBM);
         int ssplits = 1;
         int64_t sk_chunk = K;
