@@ -449,6 +449,7 @@ class GRUTower:
         self.eng = eng
         self.d = int(cfg['embedding_size'])
         self.Hd = int(cfg.get('hidden_size', self.d))
+        self.n_groups = int(cfg.get('gru_row_groups', 4))           # per-step path: row groups on parallel streams (1 = serial)
         self.persistent = bool(int(cfg.get('gru_persistent', 0)))   # 1: one launch per direction for all L steps (csrc/gru.cu); 0: one
                                                                     # tcgen05 GEMM + gate kernel per time step inside the step's CUDA graph (faster at c3 today)
         self.p_emb = float(cfg.get('dropout_prob', 0) or 0)        # nn.Dropout on the gathered rows, gru.py:29
@@ -459,6 +460,29 @@ class GRUTower:
     def flat_order(model):
         return ['gru_layers.weight_ih_l0', 'gru_layers.weight_hh_l0', 'gru_layers.bias_ih_l0', 'gru_layers.bias_hh_l0',
                 'dense.weight', 'dense.bias']
+
+    # ---- row groups of the per-step recurrence on parallel streams ----
+    def _row_groups(self, B):
+        """Contiguous row ranges (multiples of 128 rows = one GEMM stripe) whose recurrences run concurrently."""
+        G = max(1, min(self.n_groups, B // 256))
+        per = ((B + G - 1) // G + 127) // 128 * 128
+        groups = [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
+        while len(getattr(self, '_streams', [])) < len(groups):
+            self.__dict__.setdefault('_streams', []).append(torch.cuda.Stream(device=self.eng.device))
+        return groups
+
+    def _group_streams(self, groups):
+        return [(g, self._streams[i]) for i, g in enumerate(groups)]
+
+    def _fork(self, groups):
+        main = torch.cuda.current_stream()
+        for i in range(len(groups)):
+            self._streams[i].wait_stream(main)
+
+    def _join(self, groups):
+        main = torch.cuda.current_stream()
+        for i in range(len(groups)):
+            main.wait_stream(self._streams[i])
 
     def forward(self, item_seq, save=True, **_):
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
@@ -481,9 +505,19 @@ class GRUTower:
             whh_t = ops.transpose(w_hh, ws.get('gru_whh_t', (Hd, 3 * Hd)))
             ops.gru_seq_fwd(gi, whh_t, b_hh, hs, save_g, B, L, Hd)
         else:
+            # Per-step path.  Batch rows are independent along the recurrence and every per-step kernel is latency-bound (a
+            # [B, 3h] x h product gives the persistent GEMM ~100 CTAs for ~15 us), so the batch is cut into row groups whose
+            # step chains run on parallel streams -- parallel branches of the step's CUDA graph.
+            groups = self._row_groups(B)
+            gi3 = gi.view(B, L, 3 * Hd)
+            self._fork(groups)
             for t in range(L):
-                _lin_fwd(hs[t], B, Hd, w_hh, b_hh, 3 * Hd, gh, prec=prec)
-                ops.gru_gate_fwd(gi[t:], L * 3 * Hd, gh, hs[t], hs[t + 1], save_g[t], B, Hd)
+                for gidx, (b0, b1) in enumerate(groups):
+                    with torch.cuda.stream(self._streams[gidx]):
+                        n = b1 - b0
+                        _lin_fwd(hs[t][b0:b1], n, Hd, w_hh, b_hh, 3 * Hd, gh[b0:b1], prec=prec)
+                        ops.gru_gate_fwd(gi3[b0:b1, t], L * 3 * Hd, gh[b0:b1], hs[t][b0:b1], hs[t + 1][b0:b1], save_g[t][b0:b1], n, Hd)
+            self._join(groups)
         user = ws.get('user_emb', (B, d))
         _lin_fwd(hs[L], B, Hd, fp.p('dense.weight'), fp.p('dense.bias'), d, user, prec=prec)
         self.item_seq, self.x, self.hs, self.save_g = item_seq, x, hs, save_g
@@ -503,11 +537,20 @@ class GRUTower:
         if self.persistent and Hd % 32 == 0 and Hd <= 768:
             ops.gru_seq_bwd(dh, save_g, hs, w_hh, dgi, dgh_all, B, L, Hd)
         else:
+            groups = self._row_groups(B)
+            dgi3 = dgi.view(B, L, 3 * Hd)
+            dh_a, dh_b = dh, ws.get('gru_dh_b', (B, Hd))
+            self._fork(groups)
             for t in reversed(range(L)):
-                dh_prev = ws.get('gru_dh_b' if (L - t) % 2 else 'gru_dh_a', (B, Hd))
-                ops.gru_gate_bwd(dh, save_g[t], hs[t], dgi[t:], L * 3 * Hd, dgh_all[t], dh_prev, B, Hd)
-                ops.gemm(dgh_all[t], w_hh, dh_prev, B, Hd, 3 * Hd, accumulate=True, precision=prec)
+                dh_prev = dh_b if dh is dh_a else dh_a
+                for gidx, (b0, b1) in enumerate(groups):
+                    with torch.cuda.stream(self._streams[gidx]):
+                        n = b1 - b0
+                        ops.gru_gate_bwd(dh[b0:b1], save_g[t][b0:b1], hs[t][b0:b1], dgi3[b0:b1, t], L * 3 * Hd, dgh_all[t][b0:b1],
+                                         dh_prev[b0:b1], n, Hd)
+                        ops.gemm(dgh_all[t][b0:b1], w_hh, dh_prev[b0:b1], n, Hd, 3 * Hd, accumulate=True, precision=prec)
                 dh = dh_prev
+            self._join(groups)
         # weight gradients over all steps at once
         ops.gemm(dgh_all, hs, fp.g('gru_layers.weight_hh_l0'), 3 * Hd, Hd, L * B, transA=True, lda=3 * Hd, ldb=Hd,
                  accumulate=True, precision=prec)
