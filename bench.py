@@ -330,6 +330,7 @@ def main():
     ap.add_argument('--no-loss-check', action='store_true', help='N>1: skip the single-GPU cross-check of the first loss')
     ap.add_argument('--dropout', type=float, default=0.0, help='hidden/attn (SASRec) or embedding (GRU) dropout of the timed steps')
     ap.add_argument('--batch-per-gpu', type=int, default=None)
+    ap.add_argument('--set', action='append', default=[], metavar='KEY=VALUE', help='extra config keys (experiments), e.g. gru_row_groups=8')
     ap.add_argument('--shard-p2p', type=int, default=1, help='row-sharded tables: 1 = peer-memory reads over NVLink, 0 = NCCL exchange')
     ap.add_argument('--overlap', type=int, default=0, help='overlap_table_update mode (0 off, 1 early link, 2 + early update)')
     args = ap.parse_args()
@@ -363,6 +364,12 @@ def main():
                     output_path=os.path.join(ROOT, 'gpurun_out', 'bench_ckpt'), table_shard_world=world,
                     overlap_table_update=args.overlap, cuda_graph=0 if args.no_graph else 1, shard_p2p=args.shard_p2p,
                     table_init_device=1, hidden_dropout_prob=args.dropout, attn_dropout_prob=args.dropout, dropout_prob=args.dropout)
+    for kv in args.set:
+        k, _, v = kv.partition('=')
+        try:
+            cfg_args[k] = json.loads(v)
+        except ValueError:
+            cfg_args[k] = v
     cfg = argument_parser.parse_arguments(cfg_args, argv=[])
     cfg['device'] = dev
     general.init_seed(2022)
