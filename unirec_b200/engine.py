@@ -449,7 +449,8 @@ class GRUTower:
         self.eng = eng
         self.d = int(cfg['embedding_size'])
         self.Hd = int(cfg.get('hidden_size', self.d))
-        self.n_groups = int(cfg.get('gru_row_groups', 4))           # per-step path: row groups on parallel streams (1 = serial)
+        self.n_groups = int(cfg.get('gru_row_groups', 1))           # per-step path: row groups on parallel streams (measured at c3:
+                                                                    # 1 -> 9.28 ms, 4 -> 9.18 ms, 8 -> 12.0 ms per step: no gain, default serial)
         self.persistent = bool(int(cfg.get('gru_persistent', 0)))   # 1: one launch per direction for all L steps (csrc/gru.cu); 0: one
                                                                     # tcgen05 GEMM + gate kernel per time step inside the step's CUDA graph (faster at c3 today)
         self.p_emb = float(cfg.get('dropout_prob', 0) or 0)        # nn.Dropout on the gathered rows, gru.py:29
