@@ -1,4 +1,5 @@
 // ABI glue: version query and the GEMM dispatcher (exact-fp32 SIMT kernel vs tcgen05 tensor-core kernel).
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/unirec_b200.h"
 
@@ -14,6 +15,8 @@ extern "C" int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64
 // Products with at most 32 output tiles of 128 x 128 (the B-row GEMMs of the trimmed last encoder layer, M = batch size) are
 // latency-bound on the persistent tcgen05 kernel (4-32 CTAs, 13-30 us each): they go to the small-tile exact-fp32 kernel instead.
 static inline bool ur_small_product(int64_t M, int64_t N, int64_t K) {
+    static const int enabled = getenv("UR_SMALL_GEMM") ? atoi(getenv("UR_SMALL_GEMM")) : 1;      // A/B switch
+    if (!enabled) return false;
     // (long token reductions and anything above ~160 MFLOP -- e.g. the per-step GRU products -- stay on the tensor cores)
     return ((M + 127) / 128) * ((N + 127) / 128) <= 32 && K <= 4096 && M * N * K <= (int64_t)80 * 1000 * 1000;
 }

@@ -2,6 +2,7 @@
 // C[M,N] (+)= act(op(A)[M,K] * op(B)[K,N] + bias[N]);  row-major operands with leading dimensions.
 // This is the exact-fp32 path (parity bar 1e-3 is met with large margin); the tcgen05 tensor-core path for the
 // encoder's QKV/FFN GEMMs lives in gemm_tc.cu and is selected by ur_gemm_f32 when the shape qualifies.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ur {
@@ -257,7 +258,8 @@ static int gemm_simt_launch(int transA, int transB, int64_t M, int64_t N, int64_
     if (M == 0 || N == 0) return UR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     // small problems (at most 32 tiles of 128 x 128, no device-side row bound): 32 x 32 tiles over many small CTAs
-    if (!rows_dev && ((M + ur::BM - 1) / ur::BM) * ((N + ur::BN - 1) / ur::BN) <= 32 && K <= 4096 && M * N * K <= (int64_t)80 * 1000 * 1000) {
+    static const int small_enabled = getenv("UR_SMALL_GEMM") ? atoi(getenv("UR_SMALL_GEMM")) : 1;
+    if (small_enabled && !rows_dev && ((M + ur::BM - 1) / ur::BM) * ((N + ur::BN - 1) / ur::BN) <= 32 && K <= 4096 && M * N * K <= (int64_t)80 * 1000 * 1000) {
         const int sgx = (int)((N + ur::SBN - 1) / ur::SBN), sgy = (int)((M + ur::SBM - 1) / ur::SBM);
         int ssplits = 1;
         int64_t sk_chunk = K;

@@ -260,12 +260,13 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
+            int s = 0;
+            uint32_t ph = 1;                         // parity of the previous round of stage s (first round: no wait)
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 int m0, n0, kb_begin, KB;
                 decode(u, m0, n0, kb_begin, KB);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % S;
-                    if (it >= (uint32_t)S) mbar_wait(empty + s, ((it / S) - 1) & 1);
+                    if (it >= (uint32_t)S) mbar_wait(empty + s, ph);
                     uint8_t* sa = tiles + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + a_bytes;
                     mbar_expect_tx(full + s, raw_bytes);
@@ -283,13 +284,29 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                         for (int nb = 0; nb < NC / 32; ++nb)
                             tma_load_2d(sb + (size_t)nb * 32 * BK * 4, &tmB, full + s, n0 + nb * 32, kg);
                     }
+                    if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
+            // Single-thread MMA issuer.  Everything that does not change per instruction is hoisted: the issue cadence of this one
+            // thread (dependent integer instructions at ~4 cycles each) bounded the kernel at one MMA per 130-400 cycles while the
+            // tensor pipe needs ~90 per 128x128x8 MMA (ncu r2: tensor pipe 15-27% active).  Descriptors are 64-bit values whose low
+            // 14 bits hold (shared address >> 4): stage / k-step / lo-ring moves are plain additions on that field.
             uint32_t it = 0, lt = 0;
             const uint32_t idesc = make_idesc(NC, kAmn ? p.dbg_major : 0, kBmn ? p.dbg_major : 0);
+            const uint32_t tiles_u32 = smem_u32(tiles), lo_u32 = smem_u32(lo_tiles);
+            const uint64_t da0 = !kAmn ? make_desc(tiles_u32, 16, 1024) : make_desc(tiles_u32, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
+            const uint64_t db0 = !kBmn ? make_desc(tiles_u32 + a_bytes, 16, 1024)
+                                       : make_desc(tiles_u32 + a_bytes, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
+            const uint64_t ka = (uint64_t)((!kAmn ? 32u : (uint32_t)p.dbg_kstep) >> 4);      // descriptor step per k8 (16-byte units)
+            const uint64_t kb_step = (uint64_t)((!kBmn ? 32u : (uint32_t)p.dbg_kstep) >> 4);
+            const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), lo_step = (uint64_t)(raw_bytes >> 4);
+            const uint64_t lo_base = (uint64_t)((lo_u32 - tiles_u32) >> 4);                 // lo ring sits above the raw ring
+            const bool use_split = kSplit && !(p.dbg_skip & 16);
+            int s = 0, sl = 0;                       // raw / lo ring positions and their phase bits, advanced without divisions
+            uint32_t ph = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 int m0, n0, kb_begin, KB;
                 decode(u, m0, n0, kb_begin, KB);
@@ -299,31 +316,30 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + ab * (uint32_t)NC;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % S;
-                    mbar_wait((kSplit ? ready : full) + s, (it / S) & 1);
+                    mbar_wait((kSplit ? ready : full) + s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
+                    uint64_t da = da0 + (uint64_t)s * stage_step;
+                    uint64_t db = db0 + (uint64_t)s * stage_step;
+                    if (use_split) {
+                        // same layout in the lo ring: hi stage s -> lo stage sl
+                        const uint64_t lo_off = lo_base + (uint64_t)sl * lo_step - (uint64_t)s * stage_step;
 #pragma unroll
-                    for (int k8 = 0; k8 < BK / 8; ++k8) {
-                        uint64_t da, db;
-                        if (!kAmn) da = make_desc(sa + k8 * 32, 16, 1024);
-                        else da = make_desc(sa + k8 * p.dbg_kstep, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
-                        if (!kBmn) db = make_desc(sb + k8 * 32, 16, 1024);
-                        else db = make_desc(sb + k8 * p.dbg_kstep, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
-                        if (kSplit && !(p.dbg_skip & 16)) {
-                            // same layout in the lo ring: only the start-address field (16-byte units) of the descriptors moves
-                            const uint32_t la = smem_u32(lo_tiles + (size_t)(it % SL) * raw_bytes);
-                            const uint64_t lo_off = (uint64_t)(((la - sa) & 0x3FFFFu) >> 4);
-                            umma_tf32(tacc, (da & ~0x3FFFull) | (((da & 0x3FFFull) + lo_off) & 0x3FFFull), db, idesc, (kb | k8) != 0);   // a_lo * b_hi
-                            umma_tf32(tacc, da, (db & ~0x3FFFull) | (((db & 0x3FFFull) + lo_off) & 0x3FFFull), idesc, 1);              // a_hi * b_lo
-                            umma_tf32(tacc, da, db, idesc, 1);                             // a_hi * b_hi
-                        } else {
+                        for (int k8 = 0; k8 < BK / 8; ++k8) {
+                            umma_tf32(tacc, da + lo_off, db, idesc, (kb | k8) != 0);          // a_lo * b_hi
+                            umma_tf32(tacc, da, db + lo_off, idesc, 1);                       // a_hi * b_lo
+                            umma_tf32(tacc, da, db, idesc, 1);                                // a_hi * b_hi
+                            da += ka; db += kb_step;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k8 = 0; k8 < BK / 8; ++k8) {
                             umma_tf32(tacc, da, db, idesc, (kb | k8) != 0);
+                            da += ka; db += kb_step;
                         }
                     }
                     umma_commit(empty + s);          // frees this smem stage once the MMAs above have read it
-                    if (kSplit) umma_commit(lo_empty + (it % SL));
+                    if (kSplit) { umma_commit(lo_empty + sl); if (++sl == SL) sl = 0; }
+                    if (++s == S) { s = 0; ph ^= 1; }
                 }
                 umma_commit(tmem_full + ab);         // accumulator complete
                 ++lt;
@@ -422,14 +438,14 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         const int nsplit = p.split_warps * 32;
         const int n4 = (int)(raw_bytes >> 4);
         uint32_t it = 0;
+        int s = 0, sl = 0;
+        uint32_t ph = 0, lph = 1;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             int m0, n0, kb_begin, KB;
             decode(u, m0, n0, kb_begin, KB);
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = it % S;
-                mbar_wait(full + s, (it / S) & 1);
-                const int sl = it % SL;
-                if (it >= (uint32_t)SL) mbar_wait(lo_empty + sl, ((it / SL) - 1) & 1);
+                mbar_wait(full + s, ph);
+                if (it >= (uint32_t)SL) mbar_wait(lo_empty + sl, lph);
                 float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(lo_tiles + (size_t)sl * raw_bytes);
                 if (!(p.dbg_skip & 8))
@@ -445,6 +461,8 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to tcgen05.mma
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ready + s);
+                if (++s == S) { s = 0; ph ^= 1; }
+                if (++sl == SL) { sl = 0; lph ^= 1; }
             }
         }
     }
