@@ -102,6 +102,7 @@ struct Params {
     int epi_bufs;           // store buffers per epilogue warp (1 or 2)
     int lo_stages;          // 3xTF32: depth of the lo ring
     int split_warps;        // 3xTF32: number of operand-splitter warps (4 or 8)
+    int split_trunc;        // 3xTF32: 1 = hi operand is the raw tile (hardware truncation), only lo is written
     int dbg_skip;           // bring-up: bit0 skip TMA store issue, bit1 skip bias, bit2 skip smem staging
     int n_chunks, m_stripes, total_units, splits;
     const int* rows_dev; int rows_dim;   // optional device-resident token count: rows_dim 1 -> M = min(M, *rows_dev) (row-parallel GEMMs),
@@ -448,15 +449,33 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 if (it >= (uint32_t)SL) mbar_wait(lo_empty + sl, lph);
                 float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(lo_tiles + (size_t)sl * raw_bytes);
-                if (!(p.dbg_skip & 8))
+                if (!(p.dbg_skip & 8)) {
+                    if (p.split_trunc) {
+                        // The tensor pipe ignores the low 13 mantissa bits of a kind::tf32 operand, i.e. it multiplies trunc(x): the raw
+                        // tile already IS the hi operand, only lo = tf32(x - trunc(x)) has to be produced (x - trunc(x) is exact in
+                        // fp32).  Halves the splitter's shared-memory writes -- the split was the limiter of the 3xTF32 mode
+                        // (ablation r2: 59 us -> 35 us without it on the 51200 x 384 x 128 product).
 #pragma unroll 4
-                for (int i = tid; i < n4; i += nsplit) {
-                    const float4 x = hi[i];
-                    float4 h, l;
-                    h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
-                    l.x = to_tf32_rna(x.x - h.x); l.y = to_tf32_rna(x.y - h.y); l.z = to_tf32_rna(x.z - h.z); l.w = to_tf32_rna(x.w - h.w);
-                    hi[i] = h;
-                    lo[i] = l;
+                        for (int i = tid; i < n4; i += nsplit) {
+                            const float4 x = hi[i];
+                            float4 l;
+                            l.x = to_tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u));
+                            l.y = to_tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u));
+                            l.z = to_tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u));
+                            l.w = to_tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
+                            lo[i] = l;
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int i = tid; i < n4; i += nsplit) {
+                            const float4 x = hi[i];
+                            float4 h, l;
+                            h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
+                            l.x = to_tf32_rna(x.x - h.x); l.y = to_tf32_rna(x.y - h.y); l.z = to_tf32_rna(x.z - h.z); l.w = to_tf32_rna(x.w - h.w);
+                            hi[i] = h;
+                            lo[i] = l;
+                        }
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to tcgen05.mma
                 __syncwarp();
@@ -602,6 +621,8 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     p.accumulate = accumulate ? (splits > 1 ? 1 : 2) : 0;
     p.kb_per_split = kb_per_split; p.epi_bufs = epi_bufs; p.lo_stages = lo_stages;
     static const int env_sw = getenv("UR_TC_SPLIT_WARPS") ? atoi(getenv("UR_TC_SPLIT_WARPS")) : 0;
+    static const int env_trunc = getenv("UR_TC_SPLIT_TRUNC") ? atoi(getenv("UR_TC_SPLIT_TRUNC")) : 1;
+    p.split_trunc = env_trunc;
     p.split_warps = 4;      // (8 splitter warps measured no faster: the split is not the limiter, profiles/r02/gemm_split_warps.txt)
     (void)env_sw;
     static const int env_skip = getenv("UR_TC_SKIP") ? atoi(getenv("UR_TC_SKIP")) : 0;
