@@ -120,7 +120,10 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
-// Activation stages of the epilogue.  The common activations get tight unrolled loops; everything else goes through one
+// Activation stages of the epilogue.  Both precisions use the fast-intrinsic swish (ex2.approx + fast divide, ~2 ulp each, i.e.
+// 1e-6-class against a 1e-3 parity bound): the IEEE expf + division variant made the epilogue warps the limiter of the two
+// FFN products with a fused activation in 3xTF32 mode (91 -> 59 us and 121 -> 88 us; the whole GPU suite stays green).
+// The common activations get tight unrolled loops; everything else goes through one
 // out-of-line call per element.  (Inlining the 5-way switch with erff/tanhf into a 32-element unrolled loop produced ~100 KB
 // of SASS per kernel and made the epilogue instruction-fetch bound: 140 us instead of 40 us for the FFN GEMMs.)
 __device__ __noinline__ float act_fwd_generic(float x, int act) { return act_fwd(x, act); }
@@ -415,10 +418,10 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 }
                 if (p.preact) emit(&tmP, v, false, ncol, row0);
                 if (p.dact) {
-                    epilogue_act_bwd<kSplit>(v, dnext, p.act);
+                    epilogue_act_bwd<false>(v, dnext, p.act);
                     if (c0 + 64 < NC) load_dact(ncol + 64);
                 } else if (p.act != ACT_NONE) {
-                    epilogue_act_fwd<kSplit>(v, p.act);
+                    epilogue_act_fwd<false>(v, p.act);
                 }
                 const float* buf = emit(&tmC, v, p.accumulate != 0, ncol, row0);
                 if (p.colsum) {
@@ -455,16 +458,25 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                         // tile already IS the hi operand, only lo = tf32(x - trunc(x)) has to be produced (x - trunc(x) is exact in
                         // fp32).  Halves the splitter's shared-memory writes -- the split was the limiter of the 3xTF32 mode
                         // (ablation r2: 59 us -> 35 us without it on the 51200 x 384 x 128 product).
-#pragma unroll 4
-                        for (int i = tid; i < n4; i += nsplit) {
-                            const float4 x = hi[i];
+                        // (one splitter warp per SM sub-partition: the loads of four chunks are issued together so their shared-memory
+                        // latencies overlap instead of serialising load -> ALU -> store per chunk: 739 -> 640 us per layer)
+                        auto lo_of = [](const float4 x) {
                             float4 l;
                             l.x = to_tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u));
                             l.y = to_tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u));
                             l.z = to_tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u));
                             l.w = to_tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
-                            lo[i] = l;
+                            return l;
+                        };
+                        int i = tid;
+                        for (; i + 3 * nsplit < n4; i += 4 * nsplit) {
+                            float4 x[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) x[j] = hi[i + j * nsplit];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) lo[i + j * nsplit] = lo_of(x[j]);
                         }
+                        for (; i < n4; i += nsplit) lo[i] = lo_of(hi[i]);
                     } else {
 #pragma unroll 4
                         for (int i = tid; i < n4; i += nsplit) {
@@ -574,7 +586,8 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     static const int env_max_nc = getenv("UR_TC_MAX_NC") ? atoi(getenv("UR_TC_MAX_NC")) : 0;         // tuning knobs (profiles/gemm_shapes.py)
     static const int env_bufs = getenv("UR_TC_EPI_BUFS") ? atoi(getenv("UR_TC_EPI_BUFS")) : 0;
     static const int env_stages = getenv("UR_TC_STAGES") ? atoi(getenv("UR_TC_STAGES")) : 0;
-    const int max_nc = split3 ? 128 : (env_max_nc ? env_max_nc : MAX_NC);
+    static const int env_split_nc = getenv("UR_TC_SPLIT_NC") ? atoi(getenv("UR_TC_SPLIT_NC")) : 0;
+    const int max_nc = split3 ? (env_split_nc ? env_split_nc : 128) : (env_max_nc ? env_max_nc : MAX_NC);
     int NC = 0;
     for (int c = max_nc; c >= 128; c -= 128)
         if (N % c == 0) { NC = c; break; }
