@@ -16,6 +16,7 @@ Prints ONE JSON line (rank 0):
 See DESIGN.md section "Measurement".  Workloads = BASELINE.json configs c1..c5 plus the metric's own configuration (default).
 """
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -370,7 +371,8 @@ def main():
             cfg_args[k] = json.loads(v)
         except ValueError:
             cfg_args[k] = v
-    cfg = argument_parser.parse_arguments(cfg_args, argv=[])
+    with contextlib.redirect_stdout(sys.stderr):      # stdout carries the ONE JSON line only
+        cfg = argument_parser.parse_arguments(cfg_args, argv=[])
     cfg['device'] = dev
     general.init_seed(2022)
     model = general.get_class_instance(cfg['model'], 'unirec_b200/model')(cfg)
@@ -503,7 +505,8 @@ def main():
             dist.all_gather_into_tensor(buf, v.contiguous())
             gathered[k] = buf.view((-1,) + tuple(v.shape[1:]))
         if rank == 0:
-            cfg1 = argument_parser.parse_arguments(dict(cfg_args, table_shard_world=1, batch_size=B * world), argv=[])
+            with contextlib.redirect_stdout(sys.stderr):
+                cfg1 = argument_parser.parse_arguments(dict(cfg_args, table_shard_world=1, batch_size=B * world), argv=[])
             cfg1['device'] = dev
             general.init_seed(2022)
             model1 = general.get_class_instance(cfg1['model'], 'unirec_b200/model')(cfg1).to(dev)
