@@ -54,6 +54,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand read from tensor memory (lane = row of the tile, one 32-bit column per k element): D += A_tmem * B_smem
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> tensor memory: this thread's 32 values go to 32 consecutive columns of its lane (warp w owns lanes 32*(w%4)..)
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const float4 (&x)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "f"(x[0].x), "f"(x[0].y), "f"(x[0].z), "f"(x[0].w), "f"(x[1].x), "f"(x[1].y), "f"(x[1].z), "f"(x[1].w),
+          "f"(x[2].x), "f"(x[2].y), "f"(x[2].z), "f"(x[2].w), "f"(x[3].x), "f"(x[3].y), "f"(x[3].z), "f"(x[3].w),
+          "f"(x[4].x), "f"(x[4].y), "f"(x[4].z), "f"(x[4].w), "f"(x[5].x), "f"(x[5].y), "f"(x[5].z), "f"(x[5].w),
+          "f"(x[6].x), "f"(x[6].y), "f"(x[6].z), "f"(x[6].w), "f"(x[7].x), "f"(x[7].y), "f"(x[7].z), "f"(x[7].w)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float* v) {
     uint32_t r[32];
     asm volatile(
@@ -102,7 +121,9 @@ struct Params {
     int epi_bufs;           // store buffers per epilogue warp (1 or 2)
     int lo_stages;          // 3xTF32: depth of the lo ring
     int split_warps;        // 3xTF32: number of operand-splitter warps (4 or 8)
+    int a_tmem;             // 3xTF32, K-major A: hi/lo of the A tile live in tensor memory (columns 256..511), the lo ring holds B only
     int split_trunc;        // 3xTF32: 1 = hi operand is the raw tile (hardware truncation), only lo is written
+    int prof;               // bring-up: accumulate the role clocks into g_tc_prof
     int dbg_skip;           // bring-up: bit0 skip TMA store issue, bit1 skip bias, bit2 skip smem staging
     int n_chunks, m_stripes, total_units, splits;
     const int* rows_dev; int rows_dim;   // optional device-resident token count: rows_dim 1 -> M = min(M, *rows_dev) (row-parallel GEMMs),
@@ -111,6 +132,17 @@ struct Params {
 };
 
 static int g_dbg_lbo = 32 * BK * 4, g_dbg_sbo = 512, g_dbg_kstep = 1024, g_dbg_major = 1, g_dbg_layout = 1, g_dbg_tma_swz = 4;
+
+// Bring-up profile (UR_TC_PROF=1): cycles each warp role spends in its waits / its work, summed over CTAs (ur_gemm_tc_prof reads them).
+// 0 producer wait empty | 1 MMA wait ready | 2 MMA wait tmem_empty | 3 MMA issue | 4 splitter wait full | 5 splitter wait lo_empty |
+// 6 splitter work | 7 epilogue (warp 2) wait tmem_full | 8 epilogue (warp 2) work | 9 CTA lifetime | 10 k-blocks | 11 units |
+// 12 MMA instructions of a k-block (part of 3) | 13 its commits (part of 3)
+__device__ unsigned long long g_tc_prof[16];
+struct ProfClock {
+    long long t; bool on;
+    __device__ __forceinline__ ProfClock(bool enabled) : t(0), on(enabled) { if (on) t = clock64(); }
+    __device__ __forceinline__ void lap(long long& acc) { if (on) { const long long n = clock64(); acc += n - t; t = n; } }
+};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -205,8 +237,10 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
     const int SL = kSplit ? p.lo_stages : 1;              // lo ring (3xTF32): SL stages of [A_lo | B_lo], SL <= S: the TMA prefetch
                                                           // runs S deep (HBM latency), the split only SL deep (just ahead of the MMA)
     uint8_t* tiles = smem;
+    const bool a_tmem = kSplit && !kAmn && p.a_tmem;
+    const uint32_t lo_bytes = a_tmem ? b_bytes : raw_bytes;       // one lo-ring stage
     uint8_t* lo_tiles = smem + (size_t)S * stage_bytes;
-    float* epi_stage = reinterpret_cast<float*>(lo_tiles + (kSplit ? (size_t)SL * raw_bytes : 0));   // [8 warps][epi_bufs][32 x 32] swizzled
+    float* epi_stage = reinterpret_cast<float*>(lo_tiles + (kSplit ? (size_t)SL * lo_bytes : 0));   // [8 warps][epi_bufs][32 x 32] swizzled
     float* colsum_sm = epi_stage + EPI_WARPS * p.epi_bufs * EPI_TILE_FLOATS;          // [N] when p.colsum
     uint64_t* full = reinterpret_cast<uint64_t*>(colsum_sm + (p.colsum ? p.N : 0));
     uint64_t* empty = full + S;
@@ -228,7 +262,8 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
             kb_per_split = (KB_all + p.splits - 1) / p.splits;
         }
     }
-    const uint32_t tmem_cols = 2 * NC;
+    const uint32_t tmem_cols = a_tmem ? 512 : 2 * NC;       // A in tensor memory: columns 256 + 64 j hold [hi | lo] of lo-ring stage j
+    constexpr uint32_t A_TMEM_COL = 256;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -266,11 +301,16 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
             uint32_t it = 0;
             int s = 0;
             uint32_t ph = 1;                         // parity of the previous round of stage s (first round: no wait)
+            ProfClock pc(p.prof != 0);
+            long long w_empty = 0, w_rest = 0;
+            const long long t_begin = pc.t;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 int m0, n0, kb_begin, KB;
                 decode(u, m0, n0, kb_begin, KB);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
+                    pc.lap(w_rest);
                     if (it >= (uint32_t)S) mbar_wait(empty + s, ph);
+                    pc.lap(w_empty);
                     uint8_t* sa = tiles + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + a_bytes;
                     mbar_expect_tx(full + s, raw_bytes);
@@ -291,6 +331,11 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
+            if (p.prof) {
+                atomicAdd(g_tc_prof + 0, (unsigned long long)w_empty);
+                atomicAdd(g_tc_prof + 9, (unsigned long long)(clock64() - t_begin));
+                atomicAdd(g_tc_prof + 10, (unsigned long long)it);
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -308,23 +353,41 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
             const uint64_t kb_step = (uint64_t)((!kBmn ? 32u : (uint32_t)p.dbg_kstep) >> 4);
             const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), lo_step = (uint64_t)(raw_bytes >> 4);
             const uint64_t lo_base = (uint64_t)((lo_u32 - tiles_u32) >> 4);                 // lo ring sits above the raw ring
+            const uint64_t db0_lo = !kBmn ? make_desc(lo_u32, 16, 1024) : make_desc(lo_u32, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);   // a_tmem: B_lo ring
             const bool use_split = kSplit && !(p.dbg_skip & 16);
             int s = 0, sl = 0;                       // raw / lo ring positions and their phase bits, advanced without divisions
             uint32_t ph = 0;
+            ProfClock pc(p.prof != 0);
+            long long w_ready = 0, w_tmem = 0, w_issue = 0, w_mma = 0, w_commit = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 int m0, n0, kb_begin, KB;
                 decode(u, m0, n0, kb_begin, KB);
                 if (KB <= 0) continue;
                 const uint32_t ab = lt & 1;
+                pc.lap(w_issue);
                 mbar_wait(tmem_empty + ab, ((lt >> 1) & 1) ^ 1);       // passes immediately for the first use of each buffer
+                pc.lap(w_tmem);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + ab * (uint32_t)NC;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
+                    pc.lap(w_issue);
                     mbar_wait((kSplit ? ready : full) + s, ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    pc.lap(w_ready);
+                    if (!(p.dbg_skip & 32)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    pc.lap(w_issue);
                     uint64_t da = da0 + (uint64_t)s * stage_step;
                     uint64_t db = db0 + (uint64_t)s * stage_step;
-                    if (use_split) {
+                    if (use_split && a_tmem) {
+                        const uint32_t ta = tmem_base + A_TMEM_COL + (uint32_t)sl * 64u;          // hi columns; lo at +32
+                        uint64_t dbl = db0_lo + (uint64_t)sl * (uint64_t)(b_bytes >> 4);
+#pragma unroll
+                        for (int k8 = 0; k8 < BK / 8; ++k8) {
+                            umma_tf32_ts(tacc, ta + 32u + 8u * k8, db, idesc, (kb | k8) != 0);   // a_lo * b_hi
+                            umma_tf32_ts(tacc, ta + 8u * k8, dbl, idesc, 1);                      // a_hi * b_lo
+                            umma_tf32_ts(tacc, ta + 8u * k8, db, idesc, 1);                       // a_hi * b_hi
+                            db += kb_step; dbl += kb_step;
+                        }
+                    } else if (use_split) {
                         // same layout in the lo ring: hi stage s -> lo stage sl
                         const uint64_t lo_off = lo_base + (uint64_t)sl * lo_step - (uint64_t)s * stage_step;
 #pragma unroll
@@ -341,12 +404,23 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                             da += ka; db += kb_step;
                         }
                     }
+                    pc.lap(w_mma);
                     umma_commit(empty + s);          // frees this smem stage once the MMAs above have read it
-                    if (kSplit) { umma_commit(lo_empty + sl); if (++sl == SL) sl = 0; }
+                    if (kSplit) { if (!(p.dbg_skip & 64)) umma_commit(lo_empty + sl); if (++sl == SL) sl = 0; }
+                    pc.lap(w_commit);
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
                 umma_commit(tmem_full + ab);         // accumulator complete
                 ++lt;
+            }
+            if (p.prof) {
+                pc.lap(w_issue);
+                atomicAdd(g_tc_prof + 1, (unsigned long long)w_ready);
+                atomicAdd(g_tc_prof + 2, (unsigned long long)w_tmem);
+                atomicAdd(g_tc_prof + 3, (unsigned long long)(w_issue + w_mma + w_commit));
+                atomicAdd(g_tc_prof + 12, (unsigned long long)w_mma);
+                atomicAdd(g_tc_prof + 13, (unsigned long long)w_commit);
+                atomicAdd(g_tc_prof + 11, (unsigned long long)lt);
             }
         }
     } else if (warp < 2 + EPI_WARPS) {
@@ -384,6 +458,8 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
             ++nstore;
             return buf;
         };
+        ProfClock epc(p.prof != 0 && warp == 2 && lane == 0);
+        long long e_wait = 0, e_work = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             int m0, n0, kb_begin, KB;
             decode(u, m0, n0, kb_begin, KB);
@@ -397,7 +473,9 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
             };
             if (p.dact) load_dact(n0 + half * 32);
             const uint32_t ab = lt & 1;
+            epc.lap(e_work);
             mbar_wait(tmem_full + ab, (lt >> 1) & 1);
+            epc.lap(e_wait);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + ab * (uint32_t)NC + ((uint32_t)(lb * 32) << 16);
             for (int c0 = half * 32; c0 < NC; c0 += 64) {
@@ -436,6 +514,11 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
+        if (epc.on) {
+            epc.lap(e_work);
+            atomicAdd(g_tc_prof + 7, (unsigned long long)e_wait);
+            atomicAdd(g_tc_prof + 8, (unsigned long long)e_work);
+        }
     } else if (kSplit) {
         // ---------------- splitter: warps 10..13 ----------------
         const int tid = threadIdx.x - (2 + EPI_WARPS) * 32;
@@ -444,16 +527,52 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         uint32_t it = 0;
         int s = 0, sl = 0;
         uint32_t ph = 0, lph = 1;
+        ProfClock pc(p.prof != 0 && tid == 0);
+        long long w_full = 0, w_lo = 0, w_work = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             int m0, n0, kb_begin, KB;
             decode(u, m0, n0, kb_begin, KB);
             for (int kb = 0; kb < KB; ++kb, ++it) {
+                pc.lap(w_work);
                 mbar_wait(full + s, ph);
-                if (it >= (uint32_t)SL) mbar_wait(lo_empty + sl, lph);
+                pc.lap(w_full);
+                if (it >= (uint32_t)SL) mbar_wait(((p.dbg_skip & 64) ? empty : lo_empty) + sl, lph);
+                pc.lap(w_lo);
                 float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * stage_bytes);
-                float4* lo = reinterpret_cast<float4*>(lo_tiles + (size_t)sl * raw_bytes);
+                float4* lo = reinterpret_cast<float4*>(lo_tiles + (size_t)sl * lo_bytes);
                 if (!(p.dbg_skip & 8)) {
-                    if (p.split_trunc) {
+                    if (a_tmem) {
+                        // A tile -> tensor memory: thread = row (warp w reaches lanes 32 (w % 4) ..), its 32 k values are the eight
+                        // 16-byte chunks of the 128-byte swizzled row; the raw words are the hi operand (the tensor pipe truncates),
+                        // lo = tf32(x - trunc(x)).  The MMAs then read A from TMEM: no shared-memory A traffic per MMA (the kernel is
+                        // bound by the 128 B/clk shared-memory pipe: TMA fill + split + 3 operand reads per k-step).
+                        const int r = (warp & 3) * 32 + lane;
+                        const uint8_t* arow = reinterpret_cast<const uint8_t*>(hi) + r * 128;
+                        const uint32_t ta = tmem_base + A_TMEM_COL + (uint32_t)sl * 64u + ((uint32_t)((warp & 3) * 32) << 16);
+                        float4 x[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
+                        tmem_st_x32(ta, x);
+                        // (+0x1000 then the pipe's own truncation of the low 13 bits = round-to-nearest: no second mask needed)
+                        auto lo1 = [](float v) { return __uint_as_float(__float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u)) + 0x1000u); };
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) x[c] = make_float4(lo1(x[c].x), lo1(x[c].y), lo1(x[c].z), lo1(x[c].w));
+                        tmem_st_x32(ta + 32u, x);
+                        // B tile: elementwise on the raw bytes (any layout), lo into the B-only lo ring
+                        const float4* bh = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(hi) + a_bytes);
+                        const int n4b = (int)(b_bytes >> 4);
+                        int i = tid;
+                        for (; i + 3 * nsplit < n4b; i += 4 * nsplit) {
+                            float4 y[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) y[j] = bh[i + j * nsplit];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) lo[i + j * nsplit] = make_float4(lo1(y[j].x), lo1(y[j].y), lo1(y[j].z), lo1(y[j].w));
+                        }
+                        for (; i < n4b; i += nsplit) { const float4 y = bh[i]; lo[i] = make_float4(lo1(y.x), lo1(y.y), lo1(y.z), lo1(y.w)); }
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    } else if (p.split_trunc) {
                         // The tensor pipe ignores the low 13 mantissa bits of a kind::tf32 operand, i.e. it multiplies trunc(x): the raw
                         // tile already IS the hi operand, only lo = tf32(x - trunc(x)) has to be produced (x - trunc(x) is exact in
                         // fp32).  Halves the splitter's shared-memory writes -- the split was the limiter of the 3xTF32 mode
@@ -495,6 +614,12 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 if (++s == S) { s = 0; ph ^= 1; }
                 if (++sl == SL) { sl = 0; lph ^= 1; }
             }
+        }
+        if (pc.on) {
+            pc.lap(w_work);
+            atomicAdd(g_tc_prof + 4, (unsigned long long)w_full);
+            atomicAdd(g_tc_prof + 5, (unsigned long long)w_lo);
+            atomicAdd(g_tc_prof + 6, (unsigned long long)w_work);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -557,6 +682,17 @@ int ur_gemm_tc_debug_set(int lbo_bytes, int sbo_bytes, int kstep_bytes, int majo
     return UR_OK;
 }
 
+// bring-up hook: read (and optionally clear) the role clocks accumulated by launches made with UR_TC_PROF=1
+int ur_gemm_tc_prof(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16 && cudaMemcpyFromSymbol(out16, ur::tc::g_tc_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1000;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(ur::tc::g_tc_prof, z, sizeof(z)) != cudaSuccess) return -1000;
+    }
+    return UR_OK;
+}
+
 int ur_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream) {
     if (rows == 0 || cols == 0) return UR_OK;
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
@@ -597,8 +733,14 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     // one persistent CTA per SM: 3 x 64 KB (split) / 3 x 48 KB / 5 x 32 KB of operand stages + 32 or 64 KB of epilogue store buffers
     const int epi_bufs = env_bufs ? env_bufs : (split3 ? 1 : 2);
     static const int env_lo = getenv("UR_TC_LO_STAGES") ? atoi(getenv("UR_TC_LO_STAGES")) : 0;
-    const int lo_stages = split3 ? (env_lo ? env_lo : 2) : 0;
-    int stages = (int)(((split3 ? 192 : 160) * 1024) / stage_bytes) - lo_stages;
+    static const int env_atmem = getenv("UR_TC_A_TMEM") ? atoi(getenv("UR_TC_A_TMEM")) : 1;
+    static const int env_trunc = getenv("UR_TC_SPLIT_TRUNC") ? atoi(getenv("UR_TC_SPLIT_TRUNC")) : 1;
+    // K-major A in 3xTF32 mode: hi/lo of the A tile go to tensor memory (needs the 256 columns next to two 128-column accumulators)
+    const bool a_tmem = split3 && !a_mn && NC == 128 && env_atmem && env_trunc;
+    const uint32_t lo_bytes = a_tmem ? (uint32_t)NC * BK * 4 : raw_bytes;
+    const int lo_stages = split3 ? (env_lo ? env_lo : (a_tmem ? 4 : 2)) : 0;
+    if (a_tmem && lo_stages > 4) return UR_ERR_UNSUPPORTED;
+    int stages = (int)(((split3 ? 192 : 160) * 1024 - (size_t)lo_stages * lo_bytes) / stage_bytes);
     const int KB = (int)(K / BK);
     // split-K along the reduction (token) dimension when the output has too few tiles to fill the GPU (weight gradients)
     const int64_t m_stripes = (M + BM - 1) / BM;
@@ -614,7 +756,7 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     if (env_stages && stages > env_stages) stages = env_stages;
     if (stages < 2) return UR_ERR_UNSUPPORTED;
     if (split3 && lo_stages > stages) return UR_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)(stages + lo_stages) * stage_bytes + (size_t)EPI_WARPS * epi_bufs * EPI_TILE_FLOATS * sizeof(float) + (colsum ? (size_t)N * 4 : 0) +
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)lo_stages * lo_bytes + (size_t)EPI_WARPS * epi_bufs * EPI_TILE_FLOATS * sizeof(float) + (colsum ? (size_t)N * 4 : 0) +
                         (3 * stages + lo_stages + 5) * sizeof(uint64_t) + 16;
     if (smem > 227 * 1024) return UR_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmB, tmC, tmP;
@@ -634,10 +776,12 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     p.accumulate = accumulate ? (splits > 1 ? 1 : 2) : 0;
     p.kb_per_split = kb_per_split; p.epi_bufs = epi_bufs; p.lo_stages = lo_stages;
     static const int env_sw = getenv("UR_TC_SPLIT_WARPS") ? atoi(getenv("UR_TC_SPLIT_WARPS")) : 0;
-    static const int env_trunc = getenv("UR_TC_SPLIT_TRUNC") ? atoi(getenv("UR_TC_SPLIT_TRUNC")) : 1;
     p.split_trunc = env_trunc;
+    p.a_tmem = a_tmem ? 1 : 0;
     p.split_warps = 4;      // (8 splitter warps measured no faster: the split is not the limiter, profiles/r02/gemm_split_warps.txt)
     (void)env_sw;
+    static const int env_prof = getenv("UR_TC_PROF") ? atoi(getenv("UR_TC_PROF")) : 0;
+    p.prof = env_prof;
     static const int env_skip = getenv("UR_TC_SKIP") ? atoi(getenv("UR_TC_SKIP")) : 0;
     p.dbg_skip = env_skip;
     p.n_chunks = (int)(N / NC); p.m_stripes = (int)m_stripes; p.total_units = (int)(tiles * splits); p.splits = splits;
