@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UR_ABI_VERSION 3
+#define UR_ABI_VERSION 4
 
 enum { UR_LOSS_SOFTMAX = 0, UR_LOSS_BPR = 1 };
 enum { UR_ACT_NONE = 0, UR_ACT_SWISH = 1, UR_ACT_GELU = 2, UR_ACT_RELU = 3, UR_ACT_TANH = 4, UR_ACT_SIGMOID = 5 };
@@ -119,6 +119,13 @@ int ur_gemm_fused_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, c
 int ur_gemm_simt_rows_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                           int64_t ldb, float* C, int64_t ldc, const float* bias, int act, float* preact, int64_t ldp, int accumulate,
                           const int32_t* rows_dev, int rows_dim, void* stream);
+/* 3xTF32 weight lo planes (replaces the per-tile in-kernel split of the B operand; the encoder weights of
+ * unirec/model/modules.py:254-356 are constant within a step): ur_split_lo_f32 writes lo[i] = tf32(x[i] - trunc_tf32(x[i])) for a
+ * whole parameter buffer; ur_gemm_set_lo_plane registers (buffer, plane, n floats) -- a later tensor-core GEMM in 3xTF32 mode whose B
+ * operand lies inside the buffer fetches B's lo term from the plane.  n = 0 clears the registration.  The caller refreshes the plane
+ * whenever the weights change (unirec_b200.engine does so at the start of every forward pass). */
+int ur_split_lo_f32(const float* x, float* lo, int64_t n, void* stream);
+int ur_gemm_set_lo_plane(const float* base, const float* lo_plane, int64_t n);
 /* out[c][r] = in[r][c] for small weight matrices (dx = dy W is issued as an NT product on W^T) */
 int ur_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
 /* dY *= act'(preact) */

@@ -10,7 +10,7 @@ spec = importlib.util.spec_from_file_location('gemm_shapes', os.path.join(os.pat
 lib = _cabi.lib()
 lib.ur_gemm_tc_prof.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 NAMES = ['prod wait empty', 'mma wait ready', 'mma wait tmem', 'mma issue', 'split wait full', 'split wait lo_empty', 'split work',
-         'epi wait tmem_full', 'epi work', 'cta lifetime', 'k-blocks', 'units', '  mma instructions', '  mma commits']
+         'epi wait tmem_full', 'epi work', 'cta lifetime', 'k-blocks', 'units', '  mma instructions', '  mma commits', '  split A -> TMEM', '  split B']
 
 def main():
     T, d, I = 51200, 128, 512
@@ -31,7 +31,7 @@ def main():
             n = 10
             for _ in range(n): fn(P)
             lib.ur_gemm_tc_prof(out, 1)
-            v = [out[i] / n for i in range(14)]
+            v = [out[i] / n for i in range(16)]
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(20): fn(P)
@@ -41,7 +41,7 @@ def main():
             ctas = 148
             life = v[9] / ctas
             print('%s precision %d: CTA lifetime %.1f us (%.0f cycles), %.1f k-blocks, %.1f units per CTA' % (name, P, life / 1965, life, v[10] / ctas, v[11] / ctas))
-            for i in (0, 1, 2, 3, 12, 13, 4, 5, 6, 7, 8):
+            for i in (0, 1, 2, 3, 12, 13, 4, 5, 6, 14, 15, 7, 8):
                 print('    %-22s %6.1f%% of lifetime  (%.0f cycles / k-block)' % (NAMES[i], 100 * v[i] / v[9], v[i] / max(v[10], 1)))
 
 if __name__ == '__main__':

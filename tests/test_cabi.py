@@ -43,7 +43,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = _cabi.lib()
     for name in _declarations():
         assert hasattr(lib, name), name
-    assert lib.ur_version() == 3
+    assert lib.ur_version() == 4
 
 
 def test_every_entry_point_cites_the_reference():

@@ -431,6 +431,38 @@ def test_gemm_tc_3xtf32_tn_weight_grad(Mo, No, T):
     assert rel(dW, dY.double().t() @ X.double()) < X3_TOL
 
 
+@pytest.mark.parametrize('M,N,K', [(4300, 128, 128), (5000, 384, 128), (51200, 128, 512)])      # (above the small-product SIMT route)
+def test_gemm_tc_3xtf32_weight_lo_plane(M, N, K):
+    """3xTF32 with the B operand's lo term fetched from a registered lo plane (ur_split_lo_f32 + ur_gemm_set_lo_plane) instead of
+    the in-kernel split: NT (y = x W^T) and NN (dx = dy W) products of weights that live inside one parameter buffer; same bar, and
+    the very same bits as the in-kernel split (both compute lo = tf32(w - trunc(w)))."""
+    from unirec_b200 import ops
+    g = gen(31)
+    A, dY = torch.randn(M, K, generator=g).to(DEV), torch.randn(M, N, generator=g).to(DEV)
+    flat = torch.zeros(1024 + N * K + 256, device=DEV)              # the weight sits in the middle of a larger buffer
+    W = flat[1024:1024 + N * K].view(N, K)
+    W.copy_(torch.randn(N, K, generator=g) * 0.1)
+    C0, X0 = torch.empty(M, N, device=DEV), torch.empty(M, K, device=DEV)
+    ops.gemm(A, W, C0, M, N, K, transB=True, precision=3)             # in-kernel split
+    ops.gemm(dY, W, X0, M, K, N, precision=3)
+    lo = torch.empty_like(flat)
+    ops.split_lo(flat, lo)
+    ops.gemm_set_lo_plane(flat, lo)
+    try:
+        C1, X1 = torch.empty(M, N, device=DEV), torch.empty(M, K, device=DEV)
+        ops.gemm(A, W, C1, M, N, K, transB=True, precision=3)
+        ops.gemm(dY, W, X1, M, K, N, precision=3)
+        # a stale plane must show: the plane really is what the kernel reads
+        lo.zero_()
+        C2 = torch.empty(M, N, device=DEV)
+        ops.gemm(A, W, C2, M, N, K, transB=True, precision=3)
+    finally:
+        ops.gemm_set_lo_plane(None, None)
+    assert rel(C1, A.double() @ W.double().t()) < X3_TOL and rel(X1, dY.double() @ W.double()) < X3_TOL
+    assert torch.equal(C1, C0) and torch.equal(X1, X0)
+    assert not torch.equal(C2, C0) and rel(C2, A.double() @ W.double().t()) < TF32_TOL
+
+
 @pytest.mark.parametrize('precision', [0, 1, 3])
 @pytest.mark.parametrize('M,N,K', [(640, 512, 128), (5000, 128, 128)])
 def test_gemm_fused_act_bwd_and_colsum(M, N, K, precision):

@@ -35,6 +35,8 @@ SIGNATURES = {
     'ur_pack_tokens': 'pliipppppp',
     'ur_zero_tail_rows_f32': 'plipl' + 'p',
     'ur_transpose_f32': 'pllpp',
+    'ur_split_lo_f32': 'pplp',
+    'ur_gemm_set_lo_plane': 'ppl',
     'ur_act_bwd_f32': 'pplip',
     'ur_colsum_accum_f32': 'plllp' + 'p' + 'p',
     'ur_attn_fwd_f32': 'ppliiiiipp' + 'ppp' + 'pfi' + 'p',

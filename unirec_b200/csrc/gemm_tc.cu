@@ -121,6 +121,8 @@ struct Params {
     int epi_bufs;           // store buffers per epilogue warp (1 or 2)
     int lo_stages;          // 3xTF32: depth of the lo ring
     int split_warps;        // 3xTF32: number of operand-splitter warps (4 or 8)
+    int b_lo_tma;           // 3xTF32 + a_tmem: the lo part of B (a weight) is read from its precomputed lo plane by TMA (tmBlo): no B split
+    int dual_mma;           // 3xTF32: a second MMA-issuing warp (launch with 32 more threads)
     int a_tmem;             // 3xTF32, K-major A: hi/lo of the A tile live in tensor memory (columns 256..511), the lo ring holds B only
     int split_trunc;        // 3xTF32: 1 = hi operand is the raw tile (hardware truncation), only lo is written
     int prof;               // bring-up: accumulate the role clocks into g_tc_prof
@@ -136,7 +138,7 @@ static int g_dbg_lbo = 32 * BK * 4, g_dbg_sbo = 512, g_dbg_kstep = 1024, g_dbg_m
 // Bring-up profile (UR_TC_PROF=1): cycles each warp role spends in its waits / its work, summed over CTAs (ur_gemm_tc_prof reads them).
 // 0 producer wait empty | 1 MMA wait ready | 2 MMA wait tmem_empty | 3 MMA issue | 4 splitter wait full | 5 splitter wait lo_empty |
 // 6 splitter work | 7 epilogue (warp 2) wait tmem_full | 8 epilogue (warp 2) work | 9 CTA lifetime | 10 k-blocks | 11 units |
-// 12 MMA instructions of a k-block (part of 3) | 13 its commits (part of 3)
+// 12 MMA instructions of a k-block (part of 3) | 13 its commits (part of 3) | 14 splitter A tile -> TMEM | 15 splitter B tile (parts of 6)
 __device__ unsigned long long g_tc_prof[16];
 struct ProfClock {
     long long t; bool on;
@@ -222,10 +224,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
 // (second buffer, same swizzled layout -> the split is purely elementwise on the raw tile bytes), and each k-step issues
 // lo*hi + hi*lo + hi*hi into the fp32 accumulator: the dropped terms are O(2^-22), i.e. fp32-class results from the tensor pipe.
 template <bool kAmn, bool kBmn, bool kSplit>
-__global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kSplit ? 480 : 320, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const __grid_constant__ CUtensorMap tmC,
-                                                                       const __grid_constant__ CUtensorMap tmP, const Params p) {
+                                                                       const __grid_constant__ CUtensorMap tmP,
+                                                                       const __grid_constant__ CUtensorMap tmBlo, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];       // no static shared memory in this kernel: the window starts 1024-aligned
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -248,7 +251,10 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
     uint64_t* lo_empty = ready + S;                // [SL] kSplit: the MMAs that read lo stage j have completed
     uint64_t* tmem_full = lo_empty + SL;           // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* turn = tmem_empty + 2;               // [1 of 2] dual issuers: phase n completes when the MMAs of the CTA's n-th k-block are issued
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
+    const bool dual = kSplit && p.dual_mma;        // two MMA-issuing warps (1 and mma_b_warp) alternate over the k-blocks
+    const int mma_b_warp = dual ? 2 + EPI_WARPS + p.split_warps : -1;
     int KB_all = (p.K + BK - 1) / BK;
     int M_eff = p.M, m_stripes = p.m_stripes, kb_per_split = p.kb_per_split, total_units = p.total_units;
     if (p.rows_dev) {                      // packed sequences: the live token count is only known on the device
@@ -269,10 +275,11 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+        if (kSplit && p.b_lo_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
         if (p.preact) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
         for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(ready + s, kSplit ? p.split_warps : 1); }
         for (int s = 0; s < SL; ++s) mbar_init(lo_empty + s, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, dual ? 2 : 1); mbar_init(tmem_empty + i, EPI_WARPS); mbar_init(turn + i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                     pc.lap(w_empty);
                     uint8_t* sa = tiles + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + a_bytes;
-                    mbar_expect_tx(full + s, raw_bytes);
+                    mbar_expect_tx(full + s, raw_bytes + (p.b_lo_tma ? b_bytes : 0u));
                     const int kg = (kb_begin + kb) * BK;                                     // global k offset
                     if (!kAmn) {
                         tma_load_2d(sa, &tmA, full + s, kg, m0);                            // box [32 k] x [128 rows]
@@ -328,6 +335,18 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                         for (int nb = 0; nb < NC / 32; ++nb)
                             tma_load_2d(sb + (size_t)nb * 32 * BK * 4, &tmB, full + s, n0 + nb * 32, kg);
                     }
+                    if (kSplit && p.b_lo_tma) {
+                        // lo ring stage == raw ring stage (S == SL, both advance once per k-block): the MMA commit that frees raw stage s
+                        // (`empty`) is issued together with the one that frees lo stage s
+                        uint8_t* sbl = lo_tiles + (size_t)s * b_bytes;
+                        if (!kBmn) {
+                            for (int nb = 0; nb < NC / 128; ++nb)
+                                tma_load_2d(sbl + (size_t)nb * 128 * BK * 4, &tmBlo, full + s, kg, n0 + nb * 128);
+                        } else {
+                            for (int nb = 0; nb < NC / 32; ++nb)
+                                tma_load_2d(sbl + (size_t)nb * 32 * BK * 4, &tmBlo, full + s, n0 + nb * 32, kg);
+                        }
+                    }
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
@@ -337,12 +356,18 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 atomicAdd(g_tc_prof + 10, (unsigned long long)it);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == mma_b_warp) {
         if (lane == 0) {
-            // Single-thread MMA issuer.  Everything that does not change per instruction is hoisted: the issue cadence of this one
+            // MMA issuer(s): one elected thread per issuing warp.  Everything that does not change per instruction is hoisted: the issue cadence of this one
             // thread (dependent integer instructions at ~4 cycles each) bounded the kernel at one MMA per 130-400 cycles while the
             // tensor pipe needs ~90 per 128x128x8 MMA (ncu r2: tensor pipe 15-27% active).  Descriptors are 64-bit values whose low
             // 14 bits hold (shared address >> 4): stage / k-step / lo-ring moves are plain additions on that field.
+            // Two issuers (3xTF32): warp 1 takes the even k-blocks of the CTA's sequence, warp 14 the odd ones.  The issue of a k-block's
+            // MMAs blocks at the tensor pipe's pace (~67 cycles per 128x128x8), and the ~570 cycles one thread spends per k-block
+            // outside of it (barrier wait, fence, two commits: profiles/gemm_roles.py) left the pipe idle 40% of the time; with two
+            // threads that overhead runs while the other one's MMAs execute.  MMAs execute in issue order; the `turn` barrier keeps the
+            // two threads' k-blocks in sequence.
+            const int my = warp == 1 ? 0 : 1;
             uint32_t it = 0, lt = 0;
             const uint32_t idesc = make_idesc(NC, kAmn ? p.dbg_major : 0, kBmn ? p.dbg_major : 0);
             const uint32_t tiles_u32 = smem_u32(tiles), lo_u32 = smem_u32(lo_tiles);
@@ -370,8 +395,16 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + ab * (uint32_t)NC;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
+                    if (dual && (int)(it & 1) != my) {       // the other issuer's k-block: only advance the ring positions
+                        if (++sl == SL) sl = 0;
+                        if (++s == S) { s = 0; ph ^= 1; }
+                        continue;
+                    }
                     pc.lap(w_issue);
                     mbar_wait((kSplit ? ready : full) + s, ph);
+                    // strict alternation: k-block `it` is issued after k-block `it - 1` (by the other warp) -- the accumulation order,
+                    // and with it every result bit, is the single issuer's
+                    if (dual && it > 0) mbar_wait(turn, (it - 1) & 1);
                     pc.lap(w_ready);
                     if (!(p.dbg_skip & 32)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     pc.lap(w_issue);
@@ -404,6 +437,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                             da += ka; db += kb_step;
                         }
                     }
+                    if (dual) mbar_arrive(turn);
                     pc.lap(w_mma);
                     umma_commit(empty + s);          // frees this smem stage once the MMAs above have read it
                     if (kSplit) { if (!(p.dbg_skip & 64)) umma_commit(lo_empty + sl); if (++sl == SL) sl = 0; }
@@ -420,7 +454,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                 atomicAdd(g_tc_prof + 3, (unsigned long long)(w_issue + w_mma + w_commit));
                 atomicAdd(g_tc_prof + 12, (unsigned long long)w_mma);
                 atomicAdd(g_tc_prof + 13, (unsigned long long)w_commit);
-                atomicAdd(g_tc_prof + 11, (unsigned long long)lt);
+                if (my == 0) atomicAdd(g_tc_prof + 11, (unsigned long long)lt);
             }
         }
     } else if (warp < 2 + EPI_WARPS) {
@@ -528,7 +562,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
         int s = 0, sl = 0;
         uint32_t ph = 0, lph = 1;
         ProfClock pc(p.prof != 0 && tid == 0);
-        long long w_full = 0, w_lo = 0, w_work = 0;
+        long long w_full = 0, w_lo = 0, w_work = 0, w_a = 0, w_b = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             int m0, n0, kb_begin, KB;
             decode(u, m0, n0, kb_begin, KB);
@@ -558,9 +592,11 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
 #pragma unroll
                         for (int c = 0; c < 8; ++c) x[c] = make_float4(lo1(x[c].x), lo1(x[c].y), lo1(x[c].z), lo1(x[c].w));
                         tmem_st_x32(ta + 32u, x);
-                        // B tile: elementwise on the raw bytes (any layout), lo into the B-only lo ring
+                        pc.lap(w_a);
+                        // B tile: elementwise on the raw bytes (any layout), lo into the B-only lo ring -- unless the producer already
+                        // fetched it from the weight's lo plane
                         const float4* bh = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(hi) + a_bytes);
-                        const int n4b = (int)(b_bytes >> 4);
+                        const int n4b = p.b_lo_tma ? 0 : (int)(b_bytes >> 4);
                         int i = tid;
                         for (; i + 3 * nsplit < n4b; i += 4 * nsplit) {
                             float4 y[4];
@@ -570,6 +606,7 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
                             for (int j = 0; j < 4; ++j) lo[i + j * nsplit] = make_float4(lo1(y[j].x), lo1(y[j].y), lo1(y[j].z), lo1(y[j].w));
                         }
                         for (; i < n4b; i += nsplit) { const float4 y = bh[i]; lo[i] = make_float4(lo1(y.x), lo1(y.y), lo1(y.z), lo1(y.w)); }
+                        pc.lap(w_b);
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     } else if (p.split_trunc) {
@@ -619,7 +656,9 @@ __global__ void __launch_bounds__(kSplit ? 448 : 320, 1) gemm_tc_kernel(const __
             pc.lap(w_work);
             atomicAdd(g_tc_prof + 4, (unsigned long long)w_full);
             atomicAdd(g_tc_prof + 5, (unsigned long long)w_lo);
-            atomicAdd(g_tc_prof + 6, (unsigned long long)w_work);
+            atomicAdd(g_tc_prof + 6, (unsigned long long)(w_work + w_a + w_b));
+            atomicAdd(g_tc_prof + 14, (unsigned long long)w_a);
+            atomicAdd(g_tc_prof + 15, (unsigned long long)w_b);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -642,6 +681,21 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     for (int j = ty; j < 32; j += 8)
         if (bx + j < cols && by + tx < rows) out[(int64_t)(bx + j) * rows + by + tx] = t[tx][j];
 }
+
+// lo plane of a weight buffer: lo[i] = tf32-rounded (x[i] - trunc_tf32(x[i])) -- the second operand term of the 3xTF32 product, computed
+// once per forward pass for all encoder weights instead of once per staged tile in every GEMM CTA (ur_split_lo_f32)
+__global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, int64_t n4) {
+    auto lo1 = [](float v) { return __uint_as_float(__float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u)) + 0x1000u); };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        lo[i] = make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w));
+    }
+}
+
+// registered (weights, lo plane) pair: a GEMM whose B operand lies inside [base, base + n) reads B's lo term from the plane
+static const float* g_lo_base = nullptr;
+static const float* g_lo_plane = nullptr;
+static int64_t g_lo_n = 0;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -691,6 +745,21 @@ int ur_gemm_tc_prof(unsigned long long* out16, int reset) {
         if (cudaMemcpyToSymbol(ur::tc::g_tc_prof, z, sizeof(z)) != cudaSuccess) return -1000;
     }
     return UR_OK;
+}
+
+int ur_gemm_set_lo_plane(const float* base, const float* lo_plane, int64_t n) {
+    if (n < 0 || (n > 0 && (!base || !lo_plane))) return UR_ERR_BAD_ARG;
+    ur::tc::g_lo_base = n ? base : nullptr; ur::tc::g_lo_plane = n ? lo_plane : nullptr; ur::tc::g_lo_n = n;
+    return UR_OK;
+}
+
+int ur_split_lo_f32(const float* x, float* lo, int64_t n, void* stream) {
+    if (n < 0 || (n & 3) || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(lo)) & 15)) return UR_ERR_BAD_ARG;
+    if (n == 0) return UR_OK;
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > ur::kNumSMs * 8) blocks = ur::kNumSMs * 8;
+    ur::tc::split_lo_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)lo, n / 4);
+    UR_RETURN_LAST_ERROR();
 }
 
 int ur_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream) {
@@ -757,15 +826,25 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     if (stages < 2) return UR_ERR_UNSUPPORTED;
     if (split3 && lo_stages > stages) return UR_ERR_UNSUPPORTED;
     const size_t smem = (size_t)stages * stage_bytes + (size_t)lo_stages * lo_bytes + (size_t)EPI_WARPS * epi_bufs * EPI_TILE_FLOATS * sizeof(float) + (colsum ? (size_t)N * 4 : 0) +
-                        (3 * stages + lo_stages + 5) * sizeof(uint64_t) + 16;
+                        (3 * stages + lo_stages + 7) * sizeof(uint64_t) + 16;
     if (smem > 227 * 1024) return UR_ERR_UNSUPPORTED;
-    CUtensorMap tmA, tmB, tmC, tmP;
+    CUtensorMap tmA, tmB, tmC, tmP, tmBlo;
     bool ok;
     const CUtensorMapSwizzle swz_mn = (CUtensorMapSwizzle)g_dbg_tma_swz;      // 4 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
     if (!a_mn) ok = make_map(&tmA, A, M, K, lda, BK, BM);                      // A [M,K]: inner = k
     else ok = make_map(&tmA, A, K, M, lda, 32, BK, swz_mn);                    // A stored [K,M]: inner = m, rows = k
     if (!b_mn) ok = ok && make_map(&tmB, B, N, K, ldb, BK, 128);               // B [N,K]
     else ok = ok && make_map(&tmB, B, K, N, ldb, 32, BK, swz_mn);              // B stored [K,N]
+    // B inside the registered weight buffer: its lo term comes from the lo plane (same offset, same layout) by TMA
+    static const int env_blo = getenv("UR_TC_B_LO_PLANE") ? atoi(getenv("UR_TC_B_LO_PLANE")) : 1;
+    const float* B_lo = nullptr;
+    if (a_tmem && env_blo && stages == lo_stages && g_lo_n > 0 && B >= g_lo_base &&
+        B + (b_mn ? (K - 1) * ldb + N : (N - 1) * ldb + K) <= g_lo_base + g_lo_n) B_lo = g_lo_plane + (B - g_lo_base);
+    tmBlo = tmB;
+    if (B_lo) {
+        if (!b_mn) ok = ok && make_map(&tmBlo, B_lo, N, K, ldb, BK, 128);
+        else ok = ok && make_map(&tmBlo, B_lo, K, N, ldb, 32, BK, swz_mn);
+    }
     ok = ok && make_map(&tmC, C, M, N, ldc, 32, 32);                           // epilogue store boxes: 32 columns x 32 rows
     tmP = tmC;
     if (preact) ok = ok && make_map(&tmP, preact, M, N, ldp, 32, 32);
@@ -778,6 +857,9 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     static const int env_sw = getenv("UR_TC_SPLIT_WARPS") ? atoi(getenv("UR_TC_SPLIT_WARPS")) : 0;
     p.split_trunc = env_trunc;
     p.a_tmem = a_tmem ? 1 : 0;
+    p.b_lo_tma = B_lo ? 1 : 0;
+    static const int env_dual = getenv("UR_TC_DUAL_MMA") ? atoi(getenv("UR_TC_DUAL_MMA")) : 1;
+    p.dual_mma = (split3 && env_dual) ? 1 : 0;
     p.split_warps = 4;      // (8 splitter warps measured no faster: the split is not the limiter, profiles/r02/gemm_split_warps.txt)
     (void)env_sw;
     static const int env_prof = getenv("UR_TC_PROF") ? atoi(getenv("UR_TC_PROF")) : 0;
@@ -792,7 +874,7 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
 #define UR_TC_LAUNCH(AMN, BMN, SPL)                                                                                         \
     do {                                                                                                                    \
         cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-        gemm_tc_kernel<AMN, BMN, SPL><<<grid, SPL ? (2 + EPI_WARPS + p.split_warps) * 32 : 320, smem, st>>>(tmA, tmB, tmC, tmP, p);                                    \
+        gemm_tc_kernel<AMN, BMN, SPL><<<grid, SPL ? (2 + EPI_WARPS + p.split_warps + p.dual_mma) * 32 : 320, smem, st>>>(tmA, tmB, tmC, tmP, tmBlo, p);                                    \
     } while (0)
     if (split3) {
         if (a_mn) UR_TC_LAUNCH(true, true, true);

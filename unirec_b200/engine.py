@@ -241,6 +241,7 @@ class SASRecTower:
     # ---------------------------------------------------------------- forward
     def forward(self, item_seq, save=True, **_):
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
+        eng.refresh_lo_plane()
         B, L = item_seq.shape
         d, T = self.d, B * L
         item_seq = item_seq.contiguous()
@@ -487,6 +488,7 @@ class GRUTower:
 
     def forward(self, item_seq, save=True, **_):
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
+        eng.refresh_lo_plane()
         B, L = item_seq.shape
         d, Hd, prec = self.d, self.Hd, eng.prec
         table, index = eng.seq_rows_source(item_seq)
@@ -663,6 +665,9 @@ class Engine:
         rest = [n for n, p in named.items() if n not in order and id(p) not in table_ids]
         self.dense_names = order + rest        # user_bias / item_bias (and anything else) follow the tower params
         self.flat = FlatParams([(n, named[n]) for n in self.dense_names], dev)
+        # the tower weights lead the buffer: [0, _lo_span) is what the 3xTF32 lo plane covers (refresh_lo_plane)
+        self._lo_span = max([self.flat.offsets[n][0] + (self.flat.offsets[n][1] + 3) // 4 * 4 for n in order], default=0)
+        self.flat_lo = None
         for p in self.table_params():
             if not p.data.is_contiguous():
                 p.data = p.data.contiguous()
@@ -676,6 +681,19 @@ class Engine:
         self.uses_dropout = any(float(cfg.get(k, 0) or 0) > 0 for k in
                                 (('hidden_dropout_prob', 'attn_dropout_prob') if self.tower_kind == 'sasrec' else
                                  ('dropout_prob',) if self.tower_kind == 'gru' else ()))
+
+    def refresh_lo_plane(self):
+        """gemm_precision tf32x3: recompute the lo plane of the tower weights (lo = tf32(w - trunc_tf32(w))) and register it with
+        the GEMM launcher, which then fetches the lo term of every weight operand by TMA instead of splitting the staged weight tile
+        in each CTA of each GEMM (csrc/gemm_tc.cu).  Called at the start of every tower forward: weights only change between steps
+        (optimizer, load_state_dict, broadcast), so forward and backward of a step see a consistent plane."""
+        if self.prec != PRECISION_CODES['tf32x3'] or not self._lo_span:
+            return
+        if self.flat_lo is None:
+            self.flat_lo = torch.empty(self._lo_span, dtype=torch.float32, device=self.device)
+        w = self.flat.data[:self._lo_span]
+        ops.split_lo(w, self.flat_lo)
+        ops.gemm_set_lo_plane(w, self.flat_lo)
 
     def set_dropout_state(self, seed, next_step):
         """The next training forward draws the masks of (seed, next_step) -- tests replay a known mask set."""

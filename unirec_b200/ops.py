@@ -283,6 +283,22 @@ def gemm_fused(A, B, C, M, N, K, transA=False, transB=False, lda=None, ldb=None,
     return C
 
 
+def split_lo(x, lo):
+    """lo[i] = tf32(x[i] - trunc_tf32(x[i])): the lo plane of a weight buffer for the 3xTF32 GEMMs (refresh after every weight change)."""
+    n = x.numel()
+    assert lo.numel() >= n and n % 4 == 0
+    _call('ur_split_lo_f32', _f32(x), _f32(lo), n, _stream())
+    return lo
+
+
+def gemm_set_lo_plane(base, lo):
+    """Register (weight buffer, lo plane): 3xTF32 GEMMs whose B operand lies inside `base` read B's lo term from `lo`.  None clears."""
+    if base is None:
+        _call('ur_gemm_set_lo_plane', None, None, 0)
+    else:
+        _call('ur_gemm_set_lo_plane', _f32(base), _f32(lo), base.numel())
+
+
 def transpose(w, out):
     """out[c, r] = w[r, c] (small weight matrices)."""
     rows, cols = w.shape
