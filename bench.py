@@ -437,8 +437,22 @@ def main():
     # ---- eager pass 2: events around every C-ABI call -> per-kernel breakdown (launch-bound: shares, not absolutes) ----
     ops.PROFILE, ops.GEMM_LOG = {}, []
     n_prof = min(args.steps, 10)
+    gemm_roles = None
+    if os.environ.get('UR_TC_PROF'):                 # role clocks of the tcgen05 GEMM summed over this pass (csrc/gemm_tc.cu: g_tc_prof)
+        import ctypes
+        from unirec_b200 import _cabi
+        _prof = (ctypes.c_ulonglong * 16)()
+        _cabi.lib().ur_gemm_tc_prof.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+        _cabi.lib().ur_gemm_tc_prof(_prof, 1)
     ms_prof, _ = timed(n_prof, lambda i: resident[(args.warmup + i) % n_pool])
     torch.cuda.synchronize()
+    if os.environ.get('UR_TC_PROF'):
+        _cabi.lib().ur_gemm_tc_prof(_prof, 1)
+        names = ['prod_wait_empty', 'mma_wait_ready', 'mma_wait_tmem', 'mma_issue', 'split_wait_full', 'split_wait_lo_empty',
+                 'split_work', 'epi_wait_tmem_full', 'epi_work', 'cta_lifetime', 'k_blocks', 'units', 'mma_instructions',
+                 'mma_commits', 'split_a_tmem', 'split_b']
+        gemm_roles = {n: _prof[i] / n_prof for i, n in enumerate(names)}
+        gemm_roles['note'] = 'SM cycles summed over the CTAs of every tensor-core GEMM launch of one step (1965 MHz)'
     launches_per_step = sum(len(v) for v in ops.PROFILE.values()) / n_prof
     breakdown = {k: sum(a.elapsed_time(b) for a, b in v) / n_prof for k, v in ops.PROFILE.items()}
     breakdown.update(hbm_ms)                                               # the roofline kernels keep their GPU-bound timing
@@ -609,6 +623,7 @@ def main():
         'multi_gpu_loss_check': loss_check,
         'nvlink': nvlink_report(nvlink, w, B, K, L, d, world, live_frac) if nvlink else None,
         'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
+        **({'gemm_roles': gemm_roles} if gemm_roles else {}),
     }
     if not args.no_eager_baseline and world == 1:
         try:

@@ -12,6 +12,8 @@ _cal_loss (unirec/model/base/recommender.py:46-96, reco_abc.py:220-272) and its 
 """
 from typing import Dict, List, Optional
 
+import contextlib
+
 import torch
 
 from . import ops
@@ -159,19 +161,27 @@ def _lin_fwd(x, M, K, w, b, N, out, act=None, preact=None, lda=None, prec=0):
 
 
 def _lin_bwd(dy, M, N, x, K, w, dx, dw, db, lda_x=None, accumulate_dx=False, prec=0, lddy=None, lddx=None, dact=None,
-             act=None, dx_colsum=None, rows_dev=None):
+             act=None, dx_colsum=None, rows_dev=None, side=None):
     """y = x w^T + b.  dx[M,K] (+)= dy[M,N] @ w[N,K];  dw[N,K] += dy^T x;  db[N] += colsum(dy) (skipped when db is None:
     the producer of dy already accumulated it).  dact/act: dx is multiplied by act'(dact) in the GEMM epilogue, and
-    dx_colsum receives the column sums of the result (bias gradient of the layer below)."""
+    dx_colsum receives the column sums of the result (bias gradient of the layer below).  `side`: a stream for the weight / bias
+    gradient, which then runs concurrently with the input-gradient GEMM (B-row products of the trimmed last layer: each launch
+    fills a fraction of the GPU); the caller's stream waits for it before this function returns."""
+    main = torch.cuda.current_stream() if side is not None else None
+    if side is not None:
+        side.wait_stream(main)
     if dx is not None:
         if dact is not None or dx_colsum is not None:
             ops.gemm_fused(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec, dact=dact, act=act,
                            colsum=dx_colsum, rows_dev=rows_dev)
         else:
             ops.gemm(dy, w, dx, M, K, N, lda=lddy, ldc=lddx, accumulate=accumulate_dx, precision=prec, rows_dev=rows_dev)
-    ops.gemm(dy, x, dw, N, K, M, transA=True, lda=lddy or N, ldb=lda_x, accumulate=True, precision=prec, rows_dev=rows_dev)
-    if db is not None:
-        ops.colsum_accum(dy, M, N, db, ldx=lddy, rows_dev=rows_dev)
+    with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+        ops.gemm(dy, x, dw, N, K, M, transA=True, lda=lddy or N, ldb=lda_x, accumulate=True, precision=prec, rows_dev=rows_dev)
+        if db is not None:
+            ops.colsum_accum(dy, M, N, db, ldx=lddy, rows_dev=rows_dev)
+    if side is not None:
+        main.wait_stream(side)
 
 
 # ==================================================================================================
@@ -338,6 +348,12 @@ class SASRecTower:
                        drop=drops[2])
         return ('last', x, qkv, ctx, lse, z1, m1, r1, x1, hpre, hact, z2, m2, r2, xl, ql, user, drops)
 
+    def _wgrad_stream(self):
+        """Side stream for the weight-gradient products of the trimmed last layer (B rows each: a fraction of the GPU per launch)."""
+        if getattr(self, '_wside', None) is None:
+            self._wside = torch.cuda.Stream(device=self.eng.device)
+        return self._wside
+
     # ---------------------------------------------------------------- backward
     def backward(self, d_user):
         eng, fp, ws = self.eng, self.eng.flat, self.eng.ws
@@ -412,16 +428,17 @@ class SASRecTower:
         ops.add_ln_bwd(z2, fp.p(f + 'LayerNorm.weight'), m2, r2, d_user, dz2, fp.g(f + 'LayerNorm.weight'),
                        fp.g(f + 'LayerNorm.bias'), rows=B, d=d, dzsum=fp.g(f + 'dense_2.bias'), drop=drops[2], dZdrop=dy2)
         dh = ws.get('dhl', (B, I))
+        side = self._wgrad_stream()
         _lin_bwd(dy2, B, d, hact, I, fp.p(f + 'dense_2.weight'), dh, fp.g(f + 'dense_2.weight'), None, prec=prec,
-                 dact=hpre, act=self.act, dx_colsum=fp.g(f + 'dense_1.bias'))
+                 dact=hpre, act=self.act, dx_colsum=fp.g(f + 'dense_1.bias'), side=side)
         _lin_bwd(dh, B, I, x1, d, fp.p(f + 'dense_1.weight'), dz2, fp.g(f + 'dense_1.weight'), None,
-                 accumulate_dx=True, prec=prec)
+                 accumulate_dx=True, prec=prec, side=side)
         dz1 = ws.get('dz1l', (B, d))
         dy1 = ws.get('dz1ml', (B, d)) if drops[1] is not None else dz1
         ops.add_ln_bwd(z1, fp.p(a + 'LayerNorm.weight'), m1, r1, dz2, dz1, fp.g(a + 'LayerNorm.weight'),
                        fp.g(a + 'LayerNorm.bias'), rows=B, d=d, dzsum=fp.g(a + 'dense.bias'), drop=drops[1], dZdrop=dy1)
         dctx = ws.get('dctxl', (B, d))
-        _lin_bwd(dy1, B, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec)
+        _lin_bwd(dy1, B, d, ctx, d, fp.p(a + 'dense.weight'), dctx, fp.g(a + 'dense.weight'), None, prec=prec, side=side)
         dqkv, dql = ws.get('dqkv', (T, 3 * d)), ws.get('dql', (B, d))
         ops.attn_bwd(qkv, item_seq, H, self.dh, self.causal, ctx, lse, dctx, dqkv, q_only_last=True, offs=pk['offs'],
                      tok_src=pk['tok_src'], q_last=ql, dq_last=dql, drop=drops[0])
@@ -431,14 +448,19 @@ class SASRecTower:
         wq, wkv, gwq, gwkv = wqkv[:d * d], wqkv[d * d:], gwqkv[:d * d], gwqkv[d * d:]
         # input gradient: every live row gets dKV @ Wkv; the last rows add dQ @ Wq and the residual branch (dz1)
         dxf = ws.get('dz1_%d' % (i % 2), (T, d))
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            # weight / bias gradients of the projections (x comes from an LN kernel: zero rows up to the next k-block), next to
+            # the input-gradient products below
+            ops.gemm(dql, xl, gwq, d, d, B, transA=True, lda=d, ldb=d, accumulate=True, precision=prec)
+            ops.colsum_accum(dql, B, d, gbqkv[:d])
+            ops.colsum_accum(dkv, T, 2 * d, gbqkv[d:], ldx=3 * d, rows_dev=n)
         ops.gemm(dkv, wkv, dxf, T, d, 2 * d, lda=3 * d, precision=prec, rows_dev=n)
         ops.gemm(dql, wq, dz1, B, d, d, accumulate=True, precision=prec)        # dz1 <- dz1 + dQ @ Wq
         ops.scatter_add_rows(dxf, pk['last'], dz1, pad_id=-1)
-        # weight / bias gradients of the projections (x comes from an LN kernel: zero rows up to the next k-block)
         ops.gemm(dkv, x, gwkv, 2 * d, d, T, transA=True, lda=3 * d, ldb=d, accumulate=True, precision=prec, rows_dev=n)
-        ops.gemm(dql, xl, gwq, d, d, B, transA=True, lda=d, ldb=d, accumulate=True, precision=prec)
-        ops.colsum_accum(dkv, T, 2 * d, gbqkv[d:], ldx=3 * d, rows_dev=n)
-        ops.colsum_accum(dql, B, d, gbqkv[:d])
+        main.wait_stream(side)
         return dxf
 
 
