@@ -10,4 +10,7 @@ for wl in c1_mf_bpr_u10k_i5k_d64_b256 c2_sasrec_d128_seq50_items1M_k256_b1024 c3
   python bench.py --workload $wl --steps 30 --warmup 5 > gpurun_out/r2z_${wl}_n1.json 2> gpurun_out/r2z_${wl}_n1.err
 done
 python bench.py --workload c4_sasrec_d256_L4_seq200_items10M_k4096_b4096 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2z_c4_n1.json 2> gpurun_out/r2z_c4_n1.err
+python profiles/gemm_shapes.py > gpurun_out/r2z_gemm_shapes.txt 2>&1
+python profiles/small_gemm.py > gpurun_out/r2z_small_gemm.txt 2>&1
+python profiles/gemm_roles.py > gpurun_out/r2z_gemm_roles.txt 2>&1
 ls -la gpurun_out | tail -20

@@ -14,6 +14,8 @@
 // splitter of the 3xTF32 mode.  Two TMEM accumulators: the epilogue of one unit overlaps the main loop of the next.
 #include <cuda.h>
 #include <stdlib.h>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 
 namespace ur {
@@ -712,16 +714,49 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor map over a row-major matrix [rows, cols] with leading dimension ld; box = [box_cols (inner), box_rows]
+// Encoded tensor maps are cached per (base, shape, stride, box, swizzle): a training step re-issues the same ~30 products on the
+// same buffers, and in eager mode the five cuTensorMapEncodeTiled calls per launch sat between the caller's timing event and
+// the kernel.  (A descriptor only names addresses and shapes, so a cached one stays valid for as long as the key matches.)
+struct MapKey {
+    const void* base; int64_t rows, cols, ld; int box_cols, box_rows, swz;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols && box_rows == o.box_rows &&
+               swz == o.swz;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+        mix((uint64_t)k.rows); mix((uint64_t)k.cols); mix((uint64_t)k.ld);
+        mix(((uint64_t)k.box_cols << 32) | ((uint64_t)k.box_rows << 8) | (uint64_t)k.swz);
+        return h;
+    }
+};
+
 static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    static std::mutex mu;
+    const MapKey key{base, rows, cols, ld, box_cols, box_rows, (int)swz};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *map = it->second; return true; }
+    }
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() >= 4096) cache.clear();
+    cache.emplace(key, *map);
+    return true;
 }
 
 }  // namespace tc
@@ -873,7 +908,13 @@ int ur_gemm_tc_ex(int transA, int transB, int64_t M, int64_t N, int64_t K, const
     cudaStream_t st = (cudaStream_t)stream;
 #define UR_TC_LAUNCH(AMN, BMN, SPL)                                                                                         \
     do {                                                                                                                    \
-        cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        static size_t smem_set[64] = {0};                  /* per instantiation and device: the attribute is sticky */           \
+        int dev_id = 0;                                                                                                     \
+        cudaGetDevice(&dev_id);                                                                                             \
+        if (dev_id < 0 || dev_id >= 64 || smem > smem_set[dev_id]) {                                                        \
+            cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            if (dev_id >= 0 && dev_id < 64) smem_set[dev_id] = smem;                                                        \
+        }                                                                                                                   \
         gemm_tc_kernel<AMN, BMN, SPL><<<grid, SPL ? (2 + EPI_WARPS + p.split_warps + p.dual_mma) * 32 : 320, smem, st>>>(tmA, tmB, tmC, tmP, tmBlo, p);                                    \
     } while (0)
     if (split3) {
