@@ -13,6 +13,7 @@ _cal_loss (unirec/model/base/recommender.py:46-96, reco_abc.py:220-272) and its 
 from typing import Dict, List, Optional
 
 import contextlib
+import weakref
 
 import torch
 
@@ -20,6 +21,18 @@ from . import ops
 
 # 'fp32' = exact FMA (SIMT); 'tf32x3' = 3xTF32 split on tcgen05 (fp32-class accuracy); 'tf32' = single-pass TF32 tensor cores
 PRECISION_CODES = {'fp32': 0, 'tf32': 1, 'bf16': 2, 'tf32x3': 3}
+
+_LO_PLANE_OWNER = None      # id() of the engine whose weight lo plane is registered with the GEMM launcher (Engine.refresh_lo_plane)
+
+
+def _release_lo_plane_of(owner_id):
+    global _LO_PLANE_OWNER
+    if _LO_PLANE_OWNER == owner_id:
+        _LO_PLANE_OWNER = None
+        try:
+            ops.gemm_set_lo_plane(None, None)
+        except Exception:           # interpreter shutdown: the library may already be gone
+            pass
 
 
 class Workspace:
@@ -690,6 +703,7 @@ class Engine:
         # the tower weights lead the buffer: [0, _lo_span) is what the 3xTF32 lo plane covers (refresh_lo_plane)
         self._lo_span = max([self.flat.offsets[n][0] + (self.flat.offsets[n][1] + 3) // 4 * 4 for n in order], default=0)
         self.flat_lo = None
+        self._lo_finalizer = getattr(self, '_lo_finalizer', None)
         for p in self.table_params():
             if not p.data.is_contiguous():
                 p.data = p.data.contiguous()
@@ -716,6 +730,17 @@ class Engine:
         w = self.flat.data[:self._lo_span]
         ops.split_lo(w, self.flat_lo)
         ops.gemm_set_lo_plane(w, self.flat_lo)
+        # The registration is a process-wide (address range -> plane) pair: it is scoped to this forward / backward pair
+        # (release_lo_plane) and dropped with the engine, so a later tensor that happens to be allocated at these addresses
+        # can never be matched against this engine's plane.
+        global _LO_PLANE_OWNER
+        if self._lo_finalizer is None:
+            self._lo_finalizer = weakref.finalize(self, _release_lo_plane_of, id(self))
+        _LO_PLANE_OWNER = id(self)
+
+    def release_lo_plane(self):
+        """End of the window opened by refresh_lo_plane (after the tower backward, or after an inference forward)."""
+        _release_lo_plane_of(id(self))
 
     def set_dropout_state(self, seed, next_step):
         """The next training forward draws the masks of (seed, next_step) -- tests replay a known mask set."""
@@ -792,7 +817,10 @@ class Engine:
     # ---- forward / backward ---------------------------------------------------------------------
     def user_emb(self, save=False, **batch):
         self.ensure_ready()
-        return self.tower.forward(save=save, **batch)
+        user = self.tower.forward(save=save, **batch)
+        if not save:
+            self.release_lo_plane()          # inference forward: no backward will close the lo-plane window
+        return user
 
     def scores_only(self, user_emb, item_id, user_id=None):
         """_predict_layer without loss (eval / predict): recommender.py:76-96."""
@@ -910,6 +938,7 @@ class Engine:
             ops.scatter_add_scalar(fp.g('user_bias'), st['user_id'].contiguous(), dscore.contiguous(), idx_group=st['N'])
         self.rowgrad(self.table_for_target()).add(st['item_id'], st['user'], st['N'], dscore, 1)
         self.tower.backward(d_user)
+        self.release_lo_plane()
 
     def zero_dense_grads(self):
         if self.flat is not None:

@@ -418,6 +418,7 @@ class ShardedEngine(Engine):
             ops.scatter_add_scalar(self.flat.g('user_bias'), st['uid_all'], dscore.contiguous(), idx_group=st['N'])
         self.rowgrad(self.table_for_target()).add(st['keys'], st['user'], st['N'], dscore, 1, key_mask=ops.PACKED_ID_MASK)
         self.tower.backward(d_user)
+        self.release_lo_plane()
 
     def sync_dense_grads(self):
         """Encoder gradients add across ranks (global normalisation): ONE all-reduce of the flat buffer."""
